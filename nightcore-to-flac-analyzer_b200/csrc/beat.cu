@@ -1,0 +1,287 @@
+// Dynamic-programming beat tracker.  Replaces librosa.beat.beat_track(onset_envelope, sr,
+// hop_length, start_bpm) as called at tempo.py:45-49 and tempo.py:159-164 (the tempo itself comes
+// from tempo.cu; frames-per-beat = round(60·(sr/hop)/bpm) = the tempogram lag).  SURVEY Appendix A.4.
+//
+// One CTA per envelope.  All arithmetic is float64 and this file is compiled with -fmad=false so
+// that sums and products round exactly like the CPU restatement (oracle/csrc/oracle_native.c).
+// The DP is sequential in time, but frame i only looks back to [i-2·fpb, i-round(fpb/2)], so
+// round(fpb/2) consecutive frames are independent: they form one wavefront, one thread each.
+#include "ncfa_common.cuh"
+
+namespace ncfa {
+
+struct BeatWs {
+    double *onorm, *ls, *cum, *window, *pen;
+    int32_t *backlink, *tmp;
+};
+
+__device__ __forceinline__ unsigned long long f64_to_ordered(double d) {
+    unsigned long long u = (unsigned long long)__double_as_longlong(d);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double ordered_to_f64(unsigned long long u) {
+    return __longlong_as_double((long long)((u >> 63) ? (u & 0x7fffffffffffffffull) : ~u));
+}
+
+__device__ __forceinline__ bool is_localmax(const double *c, int i, int n) {
+    if (i < 1) return false;
+    const double r = c[i + 1 < n ? i + 1 : n - 1];
+    return c[i] > c[i - 1] && c[i] >= r;
+}
+
+// block-wide sum / max / min helpers (deterministic tree)
+template <typename T, typename Op>
+__device__ T block_reduce(T v, T *sh, Op op) {
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] = op(sh[threadIdx.x], sh[threadIdx.x + o]);
+        __syncthreads();
+    }
+    T r = sh[0];
+    __syncthreads();
+    return r;
+}
+
+// rank-th smallest (0-based) of {cum[i] : localmax(i)} by 8-bit radix select on ordered keys
+__device__ double select_localmax(const double *cum, int n, int rank, int *hist, unsigned long long *s_prefix,
+                                  int *s_rank) {
+    if (threadIdx.x == 0) {
+        *s_prefix = 0ull;
+        *s_rank = rank;
+    }
+    __syncthreads();
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0;
+        __syncthreads();
+        const unsigned long long prefix = *s_prefix;
+        const unsigned long long himask = (shift == 56) ? 0ull : (~0ull << (shift + 8));
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            if (is_localmax(cum, i, n)) {
+                unsigned long long key = f64_to_ordered(cum[i]);
+                if ((key & himask) == prefix) atomicAdd(&hist[(int)((key >> shift) & 0xff)], 1);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int r = *s_rank, b = 0;
+            while (b < 255 && r >= hist[b]) {
+                r -= hist[b];
+                ++b;
+            }
+            *s_rank = r;
+            *s_prefix = prefix | ((unsigned long long)b << shift);
+        }
+        __syncthreads();
+    }
+    return ordered_to_f64(*s_prefix);
+}
+
+__global__ void beat_track_kernel(const float *__restrict__ onset, const int64_t *__restrict__ onset_off,
+                                  const int32_t *__restrict__ env_len, int env_stride, const int32_t *__restrict__ lag,
+                                  double *__restrict__ ws_f64, int32_t *__restrict__ ws_i32, int max_fpb,
+                                  int32_t *__restrict__ beats_out, int max_beats, int32_t *__restrict__ n_beats) {
+    extern __shared__ double sh_d[];  // blockDim doubles
+    __shared__ int hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_rank, s_cnt, s_n0, s_n1;
+    __shared__ double s_thr;
+    const int seg = blockIdx.x;
+    const int N = env_len[seg];
+    const int fpb = lag[seg];
+    const float *on = onset + onset_off[seg];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (fpb < 2 || fpb > max_fpb || N < 2) {
+        if (tid == 0) n_beats[seg] = 0;
+        return;
+    }
+    // workspace carve-up (per segment)
+    const size_t K = 2 * (size_t)max_fpb + 1;
+    double *base = ws_f64 + (size_t)seg * (3 * (size_t)env_stride + 2 * K + 8);
+    double *onorm = base, *ls = base + env_stride, *cum = base + 2 * (size_t)env_stride;
+    double *window = base + 3 * (size_t)env_stride, *pen = window + K;
+    int32_t *backlink = ws_i32 + (size_t)seg * 2 * env_stride, *tmp = backlink + env_stride;
+
+    // ---- onsets / (std(ddof=1) + tiny)
+    double s = 0.0;
+    for (int i = tid; i < N; i += nt) s += (double)on[i];
+    const double mean = block_reduce(s, sh_d, [](double a, double b) { return a + b; }) / (double)N;
+    s = 0.0;
+    for (int i = tid; i < N; i += nt) {
+        double d = (double)on[i] - mean;
+        s += d * d;
+    }
+    const double var = block_reduce(s, sh_d, [](double a, double b) { return a + b; }) / (double)(N - 1);
+    const double denom = sqrt(var) + 2.2250738585072014e-308;
+    for (int i = tid; i < N; i += nt) onorm[i] = (double)on[i] / denom;
+
+    // ---- tables: Gaussian window exp(-½((k-fpb)·32/fpb)²) and transition penalty 100·(ln d − ln fpb)²
+    const int Kw = 2 * fpb + 1;
+    const double dfpb = (double)fpb;
+    for (int k = tid; k < Kw; k += nt) {
+        double a = ((double)(k - fpb) * 32.0) / dfpb;
+        window[k] = exp(-0.5 * (a * a));
+    }
+    const int near = (int)rint(dfpb / 2.0);  // np.round: half to even
+    const int far = 2 * fpb;
+    const double logf = log(dfpb);
+    for (int d = near + tid; d <= far; d += nt) {
+        double x = log((double)d) - logf;
+        pen[d - near] = 100.0 * (x * x);
+    }
+    __syncthreads();
+
+    // ---- local score: 'same' convolution restated with librosa's loop bounds
+    double lmax = -INFINITY;
+    for (int i = tid; i < N; i += nt) {
+        int k0 = i + fpb - N + 1;
+        if (k0 < 0) k0 = 0;
+        int k1 = i + fpb;
+        if (k1 > Kw) k1 = Kw;
+        double acc = 0.0;
+        for (int k = k0; k < k1; ++k) acc = acc + window[k] * onorm[i + fpb - k];
+        ls[i] = acc;
+        lmax = fmax(lmax, acc);
+    }
+    lmax = block_reduce(lmax, sh_d, [](double a, double b) { return fmax(a, b); });
+    const double score_thresh = 0.01 * lmax;
+    // first frame whose local score reaches the threshold: before it backlink = -1
+    int first = N;
+    for (int i = tid; i < N; i += nt)
+        if (!(ls[i] < score_thresh)) {
+            first = i;
+            break;
+        }
+    {
+        int *sh_i = reinterpret_cast<int *>(sh_d);
+        first = block_reduce(first, sh_i, [](int a, int b) { return a < b ? a : b; });
+    }
+
+    // ---- DP over wavefronts of `near` frames
+    for (int basei = 0; basei < N; basei += near) {
+        for (int j = tid; j < near; j += nt) {
+            const int i = basei + j;
+            if (i < N) {
+                double best = -INFINITY;
+                int bl = -1;
+                int lo = i - far;
+                if (lo < 0) lo = 0;
+                for (int loc = i - near; loc >= lo; --loc) {
+                    double sc = cum[loc] - pen[i - loc - near];
+                    if (sc > best) {
+                        best = sc;
+                        bl = loc;
+                    }
+                }
+                cum[i] = (bl >= 0) ? ls[i] + best : ls[i];
+                backlink[i] = (i < first) ? -1 : bl;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- last beat: last local max of cumscore with cumscore >= ½·median(local-max scores)
+    int cnt = 0;
+    for (int i = tid; i < N; i += nt) cnt += is_localmax(cum, i, N) ? 1 : 0;
+    {
+        int *sh_i = reinterpret_cast<int *>(sh_d);
+        cnt = block_reduce(cnt, sh_i, [](int a, int b) { return a + b; });
+    }
+    int tail = N - 1;
+    if (cnt > 0) {
+        const double a = select_localmax(cum, N, (cnt - 1) / 2, hist, &s_prefix, &s_rank);
+        __syncthreads();
+        const double b = select_localmax(cum, N, cnt / 2, hist, &s_prefix, &s_rank);
+        __syncthreads();
+        const double thr = 0.5 * ((a + b) / 2.0);
+        int t = -1;
+        for (int i = tid; i < N; i += nt)
+            if (is_localmax(cum, i, N) && cum[i] >= thr) t = i;  // ascending per thread: keeps the largest
+        int *sh_i = reinterpret_cast<int *>(sh_d);
+        t = block_reduce(t, sh_i, [](int a, int b) { return a > b ? a : b; });
+        if (t >= 0) tail = t;
+    }
+
+    // ---- backtrack (sequential pointer chase) and trim threshold
+    if (tid == 0) {
+        int c = 0;
+        for (int n = tail; n >= 0; n = backlink[n]) tmp[c++] = n;
+        s_cnt = c;
+        // smooth = np.convolve(ls[beats], hanning(5))[2 : N+2];  threshold = ½·sqrt(mean(smooth²))
+        const int nb = c;
+        const int jend = (nb + 4 < N + 2) ? nb + 4 : N + 2;
+        double ss = 0.0;
+        for (int j = 2; j < jend; ++j) {
+            auto x = [&](int q) -> double { return (q >= 0 && q < nb) ? ls[tmp[nb - 1 - q]] : 0.0; };
+            double v = 0.5 * x(j - 1) + 1.0 * x(j - 2) + 0.5 * x(j - 3);
+            ss += v * v;
+        }
+        const int m = jend - 2;
+        s_thr = (m > 0) ? 0.5 * sqrt(ss / (double)m) : 0.0;
+    }
+    __syncthreads();
+    const double thr = s_thr;
+    int n0 = N, n1 = -1;
+    for (int i = tid; i < N; i += nt)
+        if (ls[i] > thr) {
+            if (i < n0) n0 = i;
+            n1 = i;
+        }
+    {
+        int *sh_i = reinterpret_cast<int *>(sh_d);
+        n0 = block_reduce(n0, sh_i, [](int a, int b) { return a < b ? a : b; });
+        n1 = block_reduce(n1, sh_i, [](int a, int b) { return a > b ? a : b; });
+    }
+    if (tid == 0) {
+        const int nb = s_cnt;
+        int w = 0;
+        bool overflow = false;
+        for (int q = 0; q < nb; ++q) {
+            int b = tmp[nb - 1 - q];
+            if (b >= n0 && b <= n1) {
+                if (w < max_beats)
+                    beats_out[(size_t)seg * max_beats + w] = b;
+                else
+                    overflow = true;
+                ++w;
+            }
+        }
+        n_beats[seg] = overflow ? -1 : w;
+    }
+}
+
+static size_t beat_f64_per_seg(int max_env_len, int max_fpb) {
+    return 3 * (size_t)max_env_len + 2 * (2 * (size_t)max_fpb + 1) + 8;
+}
+
+}  // namespace ncfa
+
+using namespace ncfa;
+
+extern "C" size_t ncfa_beat_workspace_bytes(int n_seg, int max_env_len, int max_lag) {
+    if (n_seg <= 0 || max_env_len <= 0 || max_lag <= 0) return 0;
+    return align_up((size_t)n_seg * beat_f64_per_seg(max_env_len, max_lag) * 8, 256) +
+           align_up((size_t)n_seg * 2 * max_env_len * 4, 256);
+}
+
+extern "C" int ncfa_beat_track_batched(const float *d_onset, const int64_t *d_onset_off, const int32_t *d_env_len,
+                                       int n_seg, int max_env_len, const int32_t *d_lag, int max_lag,
+                                       int32_t *d_beats, int max_beats, int32_t *d_n_beats, void *d_workspace,
+                                       size_t workspace_bytes, void *stream) {
+    NCFA_REQUIRE(n_seg >= 0, "n_seg");
+    if (n_seg == 0) return NCFA_OK;
+    NCFA_REQUIRE(d_onset && d_onset_off && d_env_len && d_lag && d_beats && d_n_beats && d_workspace, "null pointer");
+    NCFA_REQUIRE(max_env_len > 0 && max_beats > 0 && max_lag > 0, "max_env_len/max_beats/max_lag");
+    if (workspace_bytes < ncfa_beat_workspace_bytes(n_seg, max_env_len, max_lag)) {
+        set_error("beat workspace too small");
+        return NCFA_E_WORKSPACE;
+    }
+    double *wf = (double *)d_workspace;
+    int32_t *wi = (int32_t *)((char *)d_workspace +
+                              align_up((size_t)n_seg * beat_f64_per_seg(max_env_len, max_lag) * 8, 256));
+    const int threads = max_env_len <= 2048 ? 64 : 256;
+    beat_track_kernel<<<n_seg, threads, threads * sizeof(double), (cudaStream_t)stream>>>(
+        d_onset, d_onset_off, d_env_len, max_env_len, d_lag, wf, wi, max_lag, d_beats, max_beats, d_n_beats);
+    NCFA_LAUNCH_OK("beat_track_kernel");
+    return NCFA_OK;
+}

@@ -1,0 +1,130 @@
+// Library plumbing: error string, version, constant tables (Hann, twiddles, Slaney mel bank).
+#include <math.h>
+#include <stdarg.h>
+#include <map>
+#include <mutex>
+#include <utility>
+#include <vector>
+#include "ncfa_common.cuh"
+
+namespace ncfa {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// ---- Slaney mel scale (librosa.filters.mel(htk=False, norm='slaney'))
+static double hz_to_mel(double f) {
+    const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = log(6.4) / 27.0;
+    return f >= min_log_hz ? min_log_mel + log(f / min_log_hz) / logstep : f / f_sp;
+}
+static double mel_to_hz(double m) {
+    const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = log(6.4) / 27.0;
+    return m >= min_log_mel ? min_log_hz * exp(logstep * (m - min_log_mel)) : f_sp * m;
+}
+
+struct DeviceTables {
+    Tables t;
+};
+static std::mutex g_mu;
+static std::map<std::pair<int, int>, DeviceTables> g_tables;
+
+template <typename T>
+static int upload(const std::vector<T> &h, const T **d) {
+    T *p = nullptr;
+    NCFA_CUDA_OK(cudaMalloc(&p, h.size() * sizeof(T)));
+    NCFA_CUDA_OK(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *d = p;
+    return NCFA_OK;
+}
+
+int get_tables(int sr, Tables *out) {
+    int dev = 0;
+    NCFA_CUDA_OK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto key = std::make_pair(dev, sr);
+    auto it = g_tables.find(key);
+    if (it != g_tables.end()) {
+        *out = it->second.t;
+        return NCFA_OK;
+    }
+    NCFA_REQUIRE(sr >= 2000 && sr <= 768000, "sample rate out of range");
+    const int n_fft = NCFA_N_FFT, n_mels = NCFA_N_MELS, n_bins = n_fft / 2 + 1;
+    const double PI = 3.14159265358979323846;
+    std::vector<float> hann(n_fft);
+    for (int i = 0; i < n_fft; ++i) hann[i] = (float)(0.5 - 0.5 * cos(2.0 * PI * i / n_fft));
+    std::vector<float2> tw1024(1024), tw2048(32);
+    for (int k1 = 0; k1 < 32; ++k1)
+        for (int n2 = 0; n2 < 32; ++n2) {
+            double a = -2.0 * PI * (double)(k1 * n2) / 1024.0;
+            tw1024[k1 * 32 + n2] = make_float2((float)cos(a), (float)sin(a));
+        }
+    for (int l = 0; l < 32; ++l) {
+        double a = -2.0 * PI * l / 2048.0;
+        tw2048[l] = make_float2((float)cos(a), (float)sin(a));
+    }
+    // mel bank
+    std::vector<double> mel_f(n_mels + 2);
+    {
+        double lo = hz_to_mel(0.0), hi = hz_to_mel(sr / 2.0);
+        double step = (hi - lo) / (n_mels + 1);
+        for (int i = 0; i < n_mels + 2; ++i) mel_f[i] = mel_to_hz(i * step + lo);
+        mel_f[n_mels + 1] = mel_to_hz(hi);
+    }
+    const double d = 1.0 / sr, val = 1.0 / (n_fft * d);
+    std::vector<float> w;
+    std::vector<int> start(n_mels + 1), bin0(n_mels);
+    for (int m = 0; m < n_mels; ++m) {
+        const double fd0 = mel_f[m + 1] - mel_f[m], fd1 = mel_f[m + 2] - mel_f[m + 1];
+        const double enorm = 2.0 / (mel_f[m + 2] - mel_f[m]);
+        int first = -1, last = -1;
+        std::vector<float> row(n_bins);
+        for (int k = 0; k < n_bins; ++k) {
+            const double f = k * val;
+            const double lower = -(mel_f[m] - f) / fd0, upper = (mel_f[m + 2] - f) / fd1;
+            const double tri = fmax(0.0, fmin(lower, upper));
+            const float w32 = (float)tri;                       // weights[i] assigned into a float32 array
+            row[k] = (float)((double)w32 * enorm);              // weights *= enorm[:, None]
+            if (row[k] != 0.0f) {
+                if (first < 0) first = k;
+                last = k;
+            }
+        }
+        start[m] = (int)w.size();
+        bin0[m] = first < 0 ? 0 : first;
+        if (first >= 0)
+            for (int k = first; k <= last; ++k) w.push_back(row[k]);
+    }
+    start[n_mels] = (int)w.size();
+    if ((int)w.size() > 2048) {
+        set_error("mel bank has %zu non-zeros (> 2048) at sr=%d", w.size(), sr);
+        return NCFA_E_OVERFLOW;
+    }
+    DeviceTables dt;
+    int rc;
+    if ((rc = upload(hann, &dt.t.hann))) return rc;
+    if ((rc = upload(tw1024, &dt.t.tw1024))) return rc;
+    if ((rc = upload(tw2048, &dt.t.tw2048))) return rc;
+    if ((rc = upload(w, &dt.t.mel_w))) return rc;
+    if ((rc = upload(start, &dt.t.mel_start))) return rc;
+    if ((rc = upload(bin0, &dt.t.mel_bin0))) return rc;
+    dt.t.mel_nnz = (int)w.size();
+    dt.t.sr = sr;
+    g_tables[key] = dt;
+    *out = dt.t;
+    return NCFA_OK;
+}
+
+}  // namespace ncfa
+
+extern "C" int ncfa_version(void) { return 100; }
+extern "C" const char *ncfa_last_error(void) { return ncfa::g_err; }
+extern "C" int ncfa_init_tables(int sr) {
+    ncfa::Tables t;
+    return ncfa::get_tables(sr, &t);
+}

@@ -1,0 +1,79 @@
+// Shared helpers for libncfa (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/ncfa.h"
+
+namespace ncfa {
+
+void set_error(const char *fmt, ...);
+
+#define NCFA_CUDA_OK(expr)                                                                          \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            ncfa::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return NCFA_E_CUDA;                                                                     \
+        }                                                                                           \
+    } while (0)
+
+#define NCFA_LAUNCH_OK(name)                                                                        \
+    do {                                                                                            \
+        cudaError_t _e = cudaGetLastError();                                                        \
+        if (_e != cudaSuccess) {                                                                    \
+            ncfa::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));                \
+            return NCFA_E_CUDA;                                                                     \
+        }                                                                                           \
+    } while (0)
+
+#define NCFA_REQUIRE(cond, msg)                                                                     \
+    do {                                                                                            \
+        if (!(cond)) {                                                                              \
+            ncfa::set_error("invalid argument: %s", msg);                                           \
+            return NCFA_E_INVALID;                                                                  \
+        }                                                                                           \
+    } while (0)
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Constant tables that live in device global memory, one set per device (see ncfa_api.cu).
+struct Tables {
+    const float *hann;        // [2048] periodic Hann, float32(float64 value)
+    const float2 *tw1024;     // [32][32]: tw[k1*32 + n2] = exp(-2πi·k1·n2/1024)
+    const float2 *tw2048;     // [32]: exp(-2πi·l/2048), l = lane
+    const float *mel_w;       // packed non-zero weights, band-major
+    const int *mel_start;     // [129] start of band m in mel_w
+    const int *mel_bin0;      // [128] first FFT bin of band m
+    int mel_nnz;
+    int sr;
+};
+int get_tables(int sr, Tables *out);
+
+// order-preserving float <-> uint encoding for atomicMax on floats
+__device__ __forceinline__ unsigned float_to_ordered(float f) {
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(unsigned u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace ncfa

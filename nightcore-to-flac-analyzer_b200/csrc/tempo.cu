@@ -1,0 +1,266 @@
+// Tempo from an onset envelope: mean inf-normalised Hann-windowed autocorrelation tempogram,
+// log-normal prior, argmax lag.  Replaces librosa.feature.tempo as called at tempo.py:63-66 and
+// inside librosa.beat.beat_track (tempo.py:45,159).  SURVEY.md Appendix A.3.
+//
+// librosa materialises an FFT autocorrelation for every frame (win_length × n_frames doubles).
+// Here nothing is materialised: with w[j] = ½(1 − cos θj), θ = 2π/W, the lag-k autocorrelation
+// of frame t is
+//   R_t[k] = ¼[(1+½c_k)·S0 − (1+c_k)·Re S1 + s_k·Im S1 + ½c_k·Re S2 − ½s_k·Im S2],
+//   S0 = Σ_j z_j,  S1 = Σ_j z_j e^{iθj},  S2 = Σ_j z_j e^{2iθj},  z_j = x[t+j]·x[t+j+k],  j < W−k,
+// and all three sums slide from t to t+1 with one remove, one add and one rotation (float64).
+// One thread owns one lag k and walks a chunk of frames; the per-frame normaliser R_t[0] is
+// computed first by direct summation (exact, no cancellation).
+#include "ncfa_common.cuh"
+
+namespace ncfa {
+
+constexpr int kLagThreads = 128;
+constexpr double kReinitRatio = 1e-4;  // re-sum exactly when the frame energy collapses
+
+// x[m], m in [0, n + 2p): envelope padded with np.pad(mode='linear_ramp', end_values=0)
+__device__ __forceinline__ double padded_env(const float *__restrict__ on, int n, int p, int m) {
+    if (m < p) return (double)(float)((double)m * ((double)on[0] / (double)p));
+    if (m < n + p) return (double)on[m - p];
+    int j = m - (n + p);
+    return (double)(float)((double)(p - 1 - j) * ((double)on[n - 1] / (double)p));
+}
+
+// trig[j] = (cos θj, sin θj), w2[j] = w[j]^2
+__global__ void tg_tables_kernel(int W, double2 *__restrict__ trig, double *__restrict__ w2) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= W) return;
+    double s, c;
+    sincospi(2.0 * (double)j / (double)W, &s, &c);
+    trig[j] = make_double2(c, s);
+    double w = 0.5 - 0.5 * c;
+    w2[j] = w * w;
+}
+
+// pass 1: r0[seg][t] = Σ_j w2[j]·x[t+j]^2
+__global__ void __launch_bounds__(256) tg_r0_kernel(const float *__restrict__ onset, const int64_t *__restrict__ onset_off,
+                                                    const int32_t *__restrict__ env_len, int env_stride, int W,
+                                                    const double *__restrict__ w2, double *__restrict__ r0) {
+    extern __shared__ double xs[];  // 256 + W
+    const int seg = blockIdx.y;
+    const int n = env_len[seg];
+    const int t0 = blockIdx.x * 256;
+    if (t0 >= n) return;
+    const float *on = onset + onset_off[seg];
+    const int p = W / 2;
+    const int span = min(256, n - t0) + W - 1;
+    for (int i = threadIdx.x; i < span; i += 256) {
+        double v = padded_env(on, n, p, t0 + i);
+        xs[i] = v * v;
+    }
+    __syncthreads();
+    const int t = t0 + threadIdx.x;
+    if (t >= n) return;
+    double acc = 0.0;
+    for (int j = 0; j < W; ++j) acc = fma(__ldg(w2 + j), xs[threadIdx.x + j], acc);
+    r0[(size_t)seg * env_stride + t] = acc;
+}
+
+// pass 2: partial[seg][chunk][k] = Σ_{t in chunk} R_t[k] / R_t[0]
+__global__ void __launch_bounds__(kLagThreads) tg_lag_kernel(const float *__restrict__ onset,
+                                                             const int64_t *__restrict__ onset_off,
+                                                             const int32_t *__restrict__ env_len, int env_stride,
+                                                             int W, int chunk, int n_chunks, int k_min,
+                                                             const double2 *__restrict__ trig,
+                                                             const double *__restrict__ r0,
+                                                             double *__restrict__ partial) {
+    extern __shared__ double xs[];  // chunk + W
+    const int seg = blockIdx.z;
+    const int n = env_len[seg];
+    const int t0 = blockIdx.y * chunk;
+    if (t0 >= n) return;
+    const int t1 = min(n, t0 + chunk);
+    const float *on = onset + onset_off[seg];
+    const int p = W / 2;
+    const int span = (t1 - t0) + W;  // x[t0 .. t1-1+W]
+    for (int i = threadIdx.x; i < span; i += kLagThreads) {
+        int m = t0 + i;
+        xs[i] = (m < n + 2 * p) ? padded_env(on, n, p, m) : 0.0;
+    }
+    __syncthreads();
+    const int k = k_min + blockIdx.x * kLagThreads + threadIdx.x;
+    const bool active = k < W;
+    const int kk = active ? k : W - 1;
+    const int L = W - kk;
+    const double2 ek = trig[kk];
+    const double2 e1 = trig[1 % W], e2 = trig[2 % W];
+    const double2 eL = trig[L % W], e2L = trig[(2 * L) % W];
+    const double q0 = 0.25 * (1.0 + 0.5 * ek.x), q1r = -0.25 * (1.0 + ek.x), q1i = 0.25 * ek.y,
+                 q2r = 0.125 * ek.x, q2i = -0.125 * ek.y;
+    const double *r0s = r0 + (size_t)seg * env_stride;
+    // the warp's longest window (smallest k) bounds the uniform init loop
+    const int Lmax = W - (k_min + blockIdx.x * kLagThreads + (threadIdx.x & ~31));
+    double S0 = 0, S1r = 0, S1i = 0, S2r = 0, S2i = 0, acc = 0, runmax = 0;
+    bool need_init = true;
+    for (int t = t0; t < t1; ++t) {
+        const double e0 = r0s[t];
+        const int o = t - t0;
+        if (e0 < kReinitRatio * runmax) need_init = true;  // warp-uniform: depends on t only
+        if (need_init) {
+            S0 = S1r = S1i = S2r = S2i = 0;
+            for (int j = 0; j < Lmax; ++j) {
+                if (j < L) {
+                    double z = xs[o + j] * xs[o + j + kk];
+                    double2 a = trig[j];
+                    int j2 = 2 * j;
+                    if (j2 >= W) j2 -= W;
+                    double2 b = trig[j2];
+                    S0 += z;
+                    S1r = fma(z, a.x, S1r);
+                    S1i = fma(z, a.y, S1i);
+                    S2r = fma(z, b.x, S2r);
+                    S2i = fma(z, b.y, S2i);
+                }
+            }
+            need_init = false;
+            runmax = e0;
+        }
+        runmax = fmax(runmax, e0);
+        const double R = q0 * S0 + q1r * S1r + q1i * S1i + q2r * S2r + q2i * S2i;
+        // librosa.util.normalize(norm=inf): frames whose max (= R_t[0]) is below tiny stay unscaled
+        const double inv = (e0 < 2.2250738585072014e-308) ? 1.0 : 1.0 / e0;
+        acc = fma(R, inv, acc);
+        if (t + 1 < t1) {
+            const double zr = xs[o] * xs[o + kk];
+            const double za = xs[o + L] * xs[o + W];
+            S0 = S0 - zr + za;
+            const double a1 = fma(za, eL.x, S1r - zr), b1 = fma(za, eL.y, S1i);
+            S1r = a1 * e1.x + b1 * e1.y;
+            S1i = b1 * e1.x - a1 * e1.y;
+            const double a2 = fma(za, e2L.x, S2r - zr), b2 = fma(za, e2L.y, S2i);
+            S2r = a2 * e2.x + b2 * e2.y;
+            S2i = b2 * e2.x - a2 * e2.y;
+        }
+    }
+    if (active) partial[((size_t)seg * n_chunks + blockIdx.y) * W + k] = acc;
+}
+
+// pass 3: tg[k] = Σ_chunks partial / n;  lag = argmax_k log1p(1e6·tg[k]) − ½(log2(bpm_k) − log2(start_bpm))²
+__global__ void __launch_bounds__(256) tg_argmax_kernel(const float *__restrict__ onset,
+                                                        const int64_t *__restrict__ onset_off,
+                                                        const int32_t *__restrict__ env_len, int W, int n_chunks,
+                                                        int chunk, int k_min, int hop, int sr,
+                                                        const double *__restrict__ start_bpm,
+                                                        const double *__restrict__ partial, int32_t *__restrict__ lag_out) {
+    __shared__ double s_best[256];
+    __shared__ int s_idx[256];
+    __shared__ int s_any;
+    const int seg = blockIdx.x;
+    const int n = env_len[seg];
+    const float *on = onset + onset_off[seg];
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
+    int any = 0;
+    for (int i = threadIdx.x; i < n; i += 256) any |= (on[i] != 0.0f);
+    if (any) s_any = 1;
+    __syncthreads();
+    if (!s_any) {
+        if (threadIdx.x == 0) lag_out[seg] = 0;
+        return;
+    }
+    const int used_chunks = (n + chunk - 1) / chunk;
+    const double l2s = log2(start_bpm[seg]);
+    double best = -INFINITY;
+    int bidx = 0x7fffffff;
+    for (int k = k_min + threadIdx.x; k < W; k += 256) {
+        double s = 0.0;
+        for (int c = 0; c < used_chunks; ++c) s += partial[((size_t)seg * n_chunks + c) * W + k];
+        const double tg = s / (double)n;
+        const double bpm = (60.0 * (double)sr) / ((double)hop * (double)k);
+        const double d = log2(bpm) - l2s;
+        const double score = log1p(1e6 * tg) + (-0.5 * (d * d));
+        if (score > best) {  // ascending k: strict > keeps the first maximum
+            best = score;
+            bidx = k;
+        }
+    }
+    s_best[threadIdx.x] = best;
+    s_idx[threadIdx.x] = bidx;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            double b2 = s_best[threadIdx.x + o];
+            int i2 = s_idx[threadIdx.x + o];
+            if (b2 > s_best[threadIdx.x] || (b2 == s_best[threadIdx.x] && i2 < s_idx[threadIdx.x])) {
+                s_best[threadIdx.x] = b2;
+                s_idx[threadIdx.x] = i2;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) lag_out[seg] = (s_idx[0] == 0x7fffffff) ? k_min : s_idx[0];
+}
+
+static int tempo_chunk(int max_env_len) { return max_env_len <= 1024 ? (max_env_len < 1 ? 1 : max_env_len) : 2048; }
+
+}  // namespace ncfa
+
+using namespace ncfa;
+
+extern "C" size_t ncfa_tempo_workspace_bytes(int n_seg, int max_env_len, int win_length) {
+    if (n_seg <= 0 || max_env_len <= 0 || win_length <= 0) return 0;
+    const int chunk = tempo_chunk(max_env_len);
+    const size_t n_chunks = (max_env_len + chunk - 1) / chunk;
+    return align_up((size_t)win_length * sizeof(double2), 256) + align_up((size_t)win_length * 8, 256) +
+           align_up((size_t)n_seg * max_env_len * 8, 256) + align_up((size_t)n_seg * n_chunks * win_length * 8, 256);
+}
+
+extern "C" int ncfa_tempo_lag_batched(const float *d_onset, const int64_t *d_onset_off, const int32_t *d_env_len,
+                                      int n_seg, int max_env_len, int hop, int sr, const double *d_start_bpm,
+                                      int32_t *d_lag, void *d_workspace, size_t workspace_bytes, void *stream) {
+    NCFA_REQUIRE(n_seg >= 0 && n_seg <= 65535, "n_seg must be in [0, 65535] per call");
+    if (n_seg == 0) return NCFA_OK;
+    NCFA_REQUIRE(d_onset && d_onset_off && d_env_len && d_start_bpm && d_lag && d_workspace, "null pointer");
+    NCFA_REQUIRE(hop > 0 && sr > 0 && max_env_len > 0, "hop/sr/max_env_len");
+    const int W = (int)floor(8.0 * (double)sr / (double)hop);  // time_to_frames(ac_size=8.0)
+    NCFA_REQUIRE(W >= 4 && W <= 5000, "win_length out of the supported range [4, 5000]");
+    if (workspace_bytes < ncfa_tempo_workspace_bytes(n_seg, max_env_len, W)) {
+        set_error("tempo workspace too small");
+        return NCFA_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int chunk = tempo_chunk(max_env_len);
+    const int n_chunks = (max_env_len + chunk - 1) / chunk;
+    char *wp = (char *)d_workspace;
+    double2 *trig = (double2 *)wp;
+    wp += align_up((size_t)W * sizeof(double2), 256);
+    double *w2 = (double *)wp;
+    wp += align_up((size_t)W * 8, 256);
+    double *r0 = (double *)wp;
+    wp += align_up((size_t)n_seg * max_env_len * 8, 256);
+    double *partial = (double *)wp;
+
+    // first lag whose bpm is below max_tempo = 320 (logprior[:max_idx] = -inf)
+    int k_min = 1;
+    while (k_min < W && !((60.0 * (double)sr) / ((double)hop * (double)k_min) < 320.0)) ++k_min;
+    NCFA_REQUIRE(k_min < W, "no admissible lag");
+
+    tg_tables_kernel<<<(W + 255) / 256, 256, 0, st>>>(W, trig, w2);
+    NCFA_LAUNCH_OK("tg_tables_kernel");
+    {
+        dim3 g((max_env_len + 255) / 256, n_seg);
+        size_t sh = (size_t)(256 + W) * 8;
+        tg_r0_kernel<<<g, 256, sh, st>>>(d_onset, d_onset_off, d_env_len, max_env_len, W, w2, r0);
+        NCFA_LAUNCH_OK("tg_r0_kernel");
+    }
+    {
+        size_t sh = (size_t)(chunk + W) * 8;
+        static size_t sh_set = 0;
+        if (sh > 48 * 1024 && sh > sh_set) {
+            NCFA_CUDA_OK(cudaFuncSetAttribute(tg_lag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+            sh_set = sh;
+        }
+        dim3 g((W - k_min + kLagThreads - 1) / kLagThreads, n_chunks, n_seg);
+        tg_lag_kernel<<<g, kLagThreads, sh, st>>>(d_onset, d_onset_off, d_env_len, max_env_len, W, chunk, n_chunks,
+                                                  k_min, trig, r0, partial);
+        NCFA_LAUNCH_OK("tg_lag_kernel");
+    }
+    tg_argmax_kernel<<<n_seg, 256, 0, st>>>(d_onset, d_onset_off, d_env_len, W, n_chunks, chunk, k_min, hop, sr,
+                                            d_start_bpm, partial, d_lag);
+    NCFA_LAUNCH_OK("tg_argmax_kernel");
+    return NCFA_OK;
+}
