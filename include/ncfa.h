@@ -39,6 +39,12 @@ extern "C" {
 int ncfa_version(void);
 const char *ncfa_last_error(void);
 
+/* Optional per-kernel timing for bench.py: while enabled, every kernel launch is bracketed by CUDA
+ * events on its stream; ncfa_profile_report() waits for them and writes "name,launches,total_ms"
+ * lines into buf, then forgets them. */
+void ncfa_profile_enable(int on);
+int ncfa_profile_report(char *buf, size_t cap);
+
 /* Build and upload the constant tables (Hann, FFT twiddles, Slaney mel bank for `sr`) on the
  * current device.  Idempotent and thread-safe; the other entry points call it lazily. */
 int ncfa_init_tables(int sr);

@@ -280,8 +280,11 @@ extern "C" int ncfa_beat_track_batched(const float *d_onset, const int64_t *d_on
     int32_t *wi = (int32_t *)((char *)d_workspace +
                               align_up((size_t)n_seg * beat_f64_per_seg(max_env_len, max_lag) * 8, 256));
     const int threads = max_env_len <= 2048 ? 64 : 256;
-    beat_track_kernel<<<n_seg, threads, threads * sizeof(double), (cudaStream_t)stream>>>(
+    {
+        ProfScope _p("beat_track_kernel", (cudaStream_t)stream);
+        beat_track_kernel<<<n_seg, threads, threads * sizeof(double), (cudaStream_t)stream>>>(
         d_onset, d_onset_off, d_env_len, max_env_len, d_lag, wf, wi, max_lag, d_beats, max_beats, d_n_beats);
+    }
     NCFA_LAUNCH_OK("beat_track_kernel");
     return NCFA_OK;
 }

@@ -68,7 +68,10 @@ extern "C" int ncfa_window_energy(const float *d_audio, const int64_t *d_seg_off
     NCFA_REQUIRE(n_seg >= 0, "n_seg");
     if (n_seg == 0) return NCFA_OK;
     NCFA_REQUIRE(d_audio && d_seg_off && d_seg_len && d_meansq, "null pointer");
-    window_energy_kernel<<<n_seg, 256, 0, (cudaStream_t)stream>>>(d_audio, d_seg_off, d_seg_len, d_meansq);
+    {
+        ProfScope _p("window_energy_kernel", (cudaStream_t)stream);
+        window_energy_kernel<<<n_seg, 256, 0, (cudaStream_t)stream>>>(d_audio, d_seg_off, d_seg_len, d_meansq);
+    }
     NCFA_LAUNCH_OK("window_energy_kernel");
     return NCFA_OK;
 }
@@ -78,8 +81,11 @@ extern "C" int ncfa_rms_frames(const float *d_audio, int64_t n, int frame_length
     NCFA_REQUIRE(n >= 0 && frame_length > 0 && hop > 0, "n/frame_length/hop");
     const int64_t n_frames = 1 + n / hop;
     NCFA_REQUIRE((n_frames + 7) / 8 < 2147483647LL, "too many frames");
-    rms_frames_kernel<<<(unsigned)((n_frames + 7) / 8), 256, 0, (cudaStream_t)stream>>>(d_audio, n, frame_length, hop,
+    {
+        ProfScope _p("rms_frames_kernel", (cudaStream_t)stream);
+        rms_frames_kernel<<<(unsigned)((n_frames + 7) / 8), 256, 0, (cudaStream_t)stream>>>(d_audio, n, frame_length, hop,
                                                                                        n_frames, d_rms);
+    }
     NCFA_LAUNCH_OK("rms_frames_kernel");
     return NCFA_OK;
 }

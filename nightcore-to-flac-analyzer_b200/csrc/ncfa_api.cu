@@ -3,6 +3,7 @@
 #include <stdarg.h>
 #include <map>
 #include <mutex>
+#include <string>
 #include <utility>
 #include <vector>
 #include "ncfa_common.cuh"
@@ -16,6 +17,33 @@ void set_error(const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+// ---- per-kernel event profiler
+struct ProfEntry {
+    const char *name;
+    cudaEvent_t e0, e1;
+};
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfEntry> g_prof;
+
+bool prof_enabled() { return g_prof_on; }
+void prof_record(const char *name, cudaStream_t st, bool begin) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (begin) {
+        ProfEntry e{name, nullptr, nullptr};
+        cudaEventCreate(&e.e0);
+        cudaEventCreate(&e.e1);
+        cudaEventRecord(e.e0, st);
+        g_prof.push_back(e);
+    } else {
+        for (size_t i = g_prof.size(); i-- > 0;)
+            if (g_prof[i].name == name) {
+                cudaEventRecord(g_prof[i].e1, st);
+                break;
+            }
+    }
 }
 
 // ---- Slaney mel scale (librosa.filters.mel(htk=False, norm='slaney'))
@@ -123,6 +151,38 @@ int get_tables(int sr, Tables *out) {
 }  // namespace ncfa
 
 extern "C" int ncfa_version(void) { return 100; }
+extern "C" void ncfa_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(ncfa::g_prof_mu);
+    ncfa::g_prof_on = on != 0;
+}
+// "name,launches,total_ms\n" per kernel, written into buf (NUL-terminated); clears the records.
+extern "C" int ncfa_profile_report(char *buf, size_t cap) {
+    using namespace ncfa;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    std::map<std::string, std::pair<int, double>> acc;
+    for (auto &e : g_prof) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(e.e1) == cudaSuccess && cudaEventElapsedTime(&ms, e.e0, e.e1) == cudaSuccess) {
+            auto &a = acc[e.name];
+            a.first += 1;
+            a.second += ms;
+        }
+        cudaEventDestroy(e.e0);
+        cudaEventDestroy(e.e1);
+    }
+    g_prof.clear();
+    std::string out;
+    char line[256];
+    for (auto &kv : acc) {
+        snprintf(line, sizeof(line), "%s,%d,%.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        out += line;
+    }
+    if (cap == 0) return NCFA_E_INVALID;
+    size_t n = out.size() < cap - 1 ? out.size() : cap - 1;
+    memcpy(buf, out.data(), n);
+    buf[n] = 0;
+    return NCFA_OK;
+}
 extern "C" const char *ncfa_last_error(void) { return ncfa::g_err; }
 extern "C" int ncfa_init_tables(int sr) {
     ncfa::Tables t;

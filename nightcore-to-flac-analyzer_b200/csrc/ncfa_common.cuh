@@ -38,6 +38,22 @@ void set_error(const char *fmt, ...);
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Optional per-kernel timing (ncfa_profile_enable): a ProfScope around a launch records two CUDA
+// events on the launch stream; ncfa_profile_report() synchronises them and sums per kernel name.
+bool prof_enabled();
+void prof_record(const char *name, cudaStream_t st, bool begin);
+struct ProfScope {
+    const char *name;
+    cudaStream_t st;
+    bool on;
+    ProfScope(const char *n, cudaStream_t s) : name(n), st(s), on(prof_enabled()) {
+        if (on) prof_record(name, st, true);
+    }
+    ~ProfScope() {
+        if (on) prof_record(name, st, false);
+    }
+};
+
 // Constant tables that live in device global memory, one set per device (see ncfa_api.cu).
 struct Tables {
     const float *hann;        // [2048] periodic Hann, float32(float64 value)

@@ -248,12 +248,18 @@ extern "C" int ncfa_onset_strength_batched(const float *d_audio, const int64_t *
         attr_done = true;
     }
     dim3 g1((frames + ft - 1) / ft, n_seg);
-    stft_logmel_kernel<<<g1, kThreads, sizeof(OnsetSmem), st>>>(d_audio, d_seg_off, d_seg_len, hop, ft, frames, tb, S,
+    {
+        ProfScope _p("stft_logmel_kernel", st);
+        stft_logmel_kernel<<<g1, kThreads, sizeof(OnsetSmem), st>>>(d_audio, d_seg_off, d_seg_len, hop, ft, frames, tb, S,
                                                                 seg_max);
+    }
     NCFA_LAUNCH_OK("stft_logmel_kernel");
     const int pad = 1 + NCFA_N_FFT / (2 * hop);
     dim3 g2((frames + 7) / 8, n_seg);
-    flux_kernel<<<g2, 256, 0, st>>>(S, seg_max, d_seg_len, hop, frames, pad, d_onset, d_onset_off);
+    {
+        ProfScope _p("flux_kernel", st);
+        flux_kernel<<<g2, 256, 0, st>>>(S, seg_max, d_seg_len, hop, frames, pad, d_onset, d_onset_off);
+    }
     NCFA_LAUNCH_OK("flux_kernel");
     return NCFA_OK;
 }

@@ -239,12 +239,18 @@ extern "C" int ncfa_tempo_lag_batched(const float *d_onset, const int64_t *d_ons
     while (k_min < W && !((60.0 * (double)sr) / ((double)hop * (double)k_min) < 320.0)) ++k_min;
     NCFA_REQUIRE(k_min < W, "no admissible lag");
 
-    tg_tables_kernel<<<(W + 255) / 256, 256, 0, st>>>(W, trig, w2);
+    {
+        ProfScope _p("tg_tables_kernel", st);
+        tg_tables_kernel<<<(W + 255) / 256, 256, 0, st>>>(W, trig, w2);
+    }
     NCFA_LAUNCH_OK("tg_tables_kernel");
     {
         dim3 g((max_env_len + 255) / 256, n_seg);
         size_t sh = (size_t)(256 + W) * 8;
-        tg_r0_kernel<<<g, 256, sh, st>>>(d_onset, d_onset_off, d_env_len, max_env_len, W, w2, r0);
+        {
+            ProfScope _p("tg_r0_kernel", st);
+            tg_r0_kernel<<<g, 256, sh, st>>>(d_onset, d_onset_off, d_env_len, max_env_len, W, w2, r0);
+        }
         NCFA_LAUNCH_OK("tg_r0_kernel");
     }
     {
@@ -255,12 +261,18 @@ extern "C" int ncfa_tempo_lag_batched(const float *d_onset, const int64_t *d_ons
             sh_set = sh;
         }
         dim3 g((W - k_min + kLagThreads - 1) / kLagThreads, n_chunks, n_seg);
-        tg_lag_kernel<<<g, kLagThreads, sh, st>>>(d_onset, d_onset_off, d_env_len, max_env_len, W, chunk, n_chunks,
+        {
+            ProfScope _p("tg_lag_kernel", st);
+            tg_lag_kernel<<<g, kLagThreads, sh, st>>>(d_onset, d_onset_off, d_env_len, max_env_len, W, chunk, n_chunks,
                                                   k_min, trig, r0, partial);
+        }
         NCFA_LAUNCH_OK("tg_lag_kernel");
     }
-    tg_argmax_kernel<<<n_seg, 256, 0, st>>>(d_onset, d_onset_off, d_env_len, W, n_chunks, chunk, k_min, hop, sr,
+    {
+        ProfScope _p("tg_argmax_kernel", st);
+        tg_argmax_kernel<<<n_seg, 256, 0, st>>>(d_onset, d_onset_off, d_env_len, W, n_chunks, chunk, k_min, hop, sr,
                                             d_start_bpm, partial, d_lag);
+    }
     NCFA_LAUNCH_OK("tg_argmax_kernel");
     return NCFA_OK;
 }

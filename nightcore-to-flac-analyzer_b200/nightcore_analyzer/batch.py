@@ -1,0 +1,255 @@
+"""
+Batched analysis of many (nightcore, source) track pairs on one GPU — the data-parallel form of
+``pipeline.run`` (pipeline.py:81-216).  Stage order and every per-pair decision follow the
+reference; only the loop structure differs: each stage runs once over all pairs of the batch.
+
+  stage 0  upload: all tracks of the batch in one HBM buffer (pinned staging → one H2D copy)
+  stage 1  strip_silence bounds          (framed RMS kernel; pipeline.py:91-104)
+  stage 2  window energies + gate        (float64 reduction; pipeline.py:127-146)
+  stage 3  pitch: chroma shift per chunk (pipeline.py:149-159)            [when compute_pitch]
+  stage 4  source windows → tempo        (pipeline.py:169)
+  stage 5  prior = median(src)·dur ratio (host scalar per pair; pipeline.py:174-178)
+  stage 6  nightcore windows → tempo     (pipeline.py:186)
+  stage 7  hop-64 whole-track beat pass  (pipeline.py:204-205)
+  stage 8  bootstraps: tempo, pitch, IBI (consensus.py:243-312) — three batched launches
+  stage 9  host: AnalysisResult per pair (classification, warnings, rubberband strings)
+
+Pairs are independent; a failing pair (all windows gated away, too few tempo windows) yields its
+exception object in the result list and does not disturb the others.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _engine, consensus, tempo as _tempo
+from .io import ENERGY_GATE_DB, HOP_SEC, SAMPLE_RATE, SILENCE_STRIP_DB, WINDOW_SEC, _db_from_meansq
+
+
+@dataclass
+class StagedBatch:
+    """Tracks of a batch resident in HBM.  Track 2i is pair i's nightcore, 2i+1 its source."""
+    audio: torch.Tensor          # float32, all tracks, 4-sample aligned starts
+    off: np.ndarray              # int64 [2P] sample offset of each track
+    length: np.ndarray           # int64 [2P] samples
+    sr: int
+    h2d_bytes: int
+
+    @property
+    def n_pairs(self) -> int:
+        return len(self.off) // 2
+
+
+def stage_pairs(pairs: Sequence[Tuple[np.ndarray, np.ndarray]], sr: int = SAMPLE_RATE,
+                pinned: Optional[torch.Tensor] = None) -> StagedBatch:
+    """Copy [(nc_audio, src_audio), ...] into one device buffer (through pinned host memory)."""
+    eng = _engine.get_engine()
+    tracks = [np.asarray(t, dtype=np.float32) for p in pairs for t in p]
+    length = np.array([len(t) for t in tracks], dtype=np.int64)
+    padded = (length + 3) // 4 * 4
+    off = np.zeros(len(tracks), dtype=np.int64)
+    if len(tracks) > 1:
+        off[1:] = np.cumsum(padded)[:-1]
+    total = int(padded.sum()) if len(tracks) else 0
+    if pinned is None or pinned.numel() < max(total, 4):
+        pinned = torch.empty(max(total, 4), dtype=torch.float32, pin_memory=True)
+    hn = pinned.numpy()
+    for t, o in zip(tracks, off):
+        hn[o : o + len(t)] = t
+    audio = pinned[: max(total, 4)].to(eng.device, non_blocking=True)
+    return StagedBatch(audio=audio, off=off, length=length, sr=sr, h2d_bytes=4 * total)
+
+
+def _window_starts(n: int, win_n: int, hop_n: int) -> np.ndarray:
+    """io.py:94-110: starts while start + win_n <= n."""
+    if win_n <= 0 or n < win_n:
+        return np.zeros(0, dtype=np.int64)
+    return np.arange(0, n - win_n + 1, max(hop_n, 1), dtype=np.int64) if hop_n > 0 else np.zeros(0, dtype=np.int64)
+
+
+def analyse_staged(batch: StagedBatch, *, window_sec: float = WINDOW_SEC, hop_sec: float = HOP_SEC,
+                   energy_gate_db: float = ENERGY_GATE_DB, silence_strip_db: Optional[float] = SILENCE_STRIP_DB,
+                   compute_pitch: bool = True, compute_ibi: bool = True, stats: Optional[dict] = None,
+                   ) -> List[Union[consensus.AnalysisResult, Exception]]:
+    eng = _engine.get_engine()
+    d2h0 = eng.d2h_bytes
+    sr = batch.sr
+    P = batch.n_pairs
+    n_tracks = 2 * P
+    t_off = batch.off.copy()
+    t_len = batch.length.copy()
+    failures: List[Optional[Exception]] = [None] * P
+
+    # ---- stage 1: strip_silence (io.py:58-79) — bounds only; the samples never move
+    if silence_strip_db is not None and n_tracks:
+        rms_list = [eng.rms_frames_dev(batch.audio[int(o):], int(n), 2048, 512) if n > 0 else None
+                    for o, n in zip(t_off, t_len)]
+        amin = 1e-5
+        for k, r in enumerate(rms_list):
+            if r is None:
+                continue
+            mag = np.abs(eng.to_host(r))
+            ref = np.max(mag)
+            db = 10.0 * np.log10(np.maximum(amin ** 2, mag ** 2)) - 10.0 * np.log10(np.maximum(amin ** 2, ref ** 2))
+            ns = np.flatnonzero(db > -silence_strip_db)
+            if ns.size:
+                s, e = int(ns[0] * 512), min(int(t_len[k]), int((ns[-1] + 1) * 512))
+            else:
+                s, e = 0, 0
+            t_off[k] += s
+            t_len[k] = e - s
+
+    # ---- stage 2: windows, float64 energies, gate (io.py:82-126)
+    win_n, hop_n = int(window_sec * sr), int(hop_sec * sr)
+    seg_track, seg_off = [], []
+    for k in range(n_tracks):
+        st = _window_starts(int(t_len[k]), win_n, hop_n)
+        seg_track.append(np.full(len(st), k, dtype=np.int64))
+        seg_off.append(t_off[k] + st)
+    seg_track = np.concatenate(seg_track) if seg_track else np.zeros(0, np.int64)
+    seg_off = np.concatenate(seg_off) if seg_off else np.zeros(0, np.int64)
+    seg_len = np.full(len(seg_off), win_n, dtype=np.int32)
+    if len(seg_off):
+        ms = eng.window_energy_dev(batch.audio, eng.to_dev(seg_off), eng.to_dev(seg_len)).cpu().numpy()
+        energy_db = np.array([_db_from_meansq(float(m)) for m in ms])
+    else:
+        energy_db = np.zeros(0)
+    cnt = np.bincount(seg_track, minlength=n_tracks) if len(seg_track) else np.zeros(n_tracks, np.int64)
+    first = np.concatenate([[0], np.cumsum(cnt)[:-1]]) if n_tracks else np.zeros(0, np.int64)
+    peak = np.full(n_tracks, -np.inf)
+    has = cnt > 0
+    if has.any():
+        peak[has] = np.maximum.reduceat(energy_db, first[has])
+    keep = energy_db >= peak[seg_track] + energy_gate_db if len(seg_track) else np.zeros(0, dtype=bool)
+    n_win_kept = np.bincount(seg_track[keep], minlength=n_tracks) if len(seg_track) else np.zeros(n_tracks, np.int64)
+    for i in range(P):
+        if n_win_kept[2 * i] == 0 or n_win_kept[2 * i + 1] == 0:
+            failures[i] = RuntimeError(
+                "All windows were discarded by the energy gate.  "
+                "Try raising --energy-gate (e.g. --energy-gate -60)."
+            )
+    alive = np.array([failures[i] is None for i in range(P)], dtype=bool)
+
+    # ---- stage 3: pitch (pitch.py:100-173), one batched pass over all chunk pairs
+    src_hz: List[list] = [[] for _ in range(P)]
+    nc_hz: List[list] = [[] for _ in range(P)]
+    pitch_method: Optional[str] = None
+    if compute_pitch:
+        from . import pitch as _pitch
+        pitch_method = "chroma_xcorr"
+        jobs = [(i, t_off[2 * i + 1], t_len[2 * i + 1], t_off[2 * i], t_len[2 * i]) for i in range(P) if alive[i]]
+        shifts = _pitch.chroma_shifts_staged(batch.audio, jobs, sr)
+        for (i, *_), st in zip(jobs, shifts):
+            src_hz[i], nc_hz[i] = _pitch.hz_lists(st)
+
+    # ---- stage 4: source windows (120 BPM prior)
+    def run_tempo(sel: np.ndarray, bpm: np.ndarray):
+        if len(sel) == 0:
+            return np.zeros(0, np.int32), np.zeros(0, np.int32)
+        _, _, _, lag, _, n_beats = eng.tempo_segments_dev(batch.audio, seg_off[sel], seg_len[sel], bpm,
+                                                          _tempo.HOP_LENGTH, sr)
+        return eng.to_host(lag), eng.to_host(n_beats)
+
+    is_src = (seg_track % 2) == 1
+    pair_of = seg_track // 2
+    sel_src = np.flatnonzero(keep & is_src & alive[pair_of])
+    lag_s, nb_s = run_tempo(sel_src, np.full(len(sel_src), 120.0))
+    src_tempos: List[list] = [[] for _ in range(P)]
+    for j, s in enumerate(sel_src):
+        src_tempos[pair_of[s]].append(_tempo._consensus(int(lag_s[j]), int(nb_s[j]), sr, _tempo.HOP_LENGTH))
+
+    # ---- stage 5: per-pair prior (pipeline.py:171-178)
+    nc_dur = t_len[0::2] / sr
+    src_dur = t_len[1::2] / sr
+    prior = np.full(P, 120.0)
+    for i in range(P):
+        valid = [t for t in src_tempos[i] if t is not None]
+        if valid and nc_dur[i] > 0 and src_dur[i] > 0:
+            prior[i] = float(np.median(valid)) * (src_dur[i] / nc_dur[i])
+
+    # ---- stage 6: nightcore windows with the pair's prior
+    sel_nc = np.flatnonzero(keep & ~is_src & alive[pair_of])
+    lag_n, nb_n = run_tempo(sel_nc, prior[pair_of[sel_nc]] if len(sel_nc) else np.zeros(0))
+    nc_tempos: List[list] = [[] for _ in range(P)]
+    for j, s in enumerate(sel_nc):
+        nc_tempos[pair_of[s]].append(_tempo._consensus(int(lag_n[j]), int(nb_n[j]), sr, _tempo.HOP_LENGTH))
+
+    # ---- stage 7: hop-64 whole-track pass (tempo.py:120-173) for every live pair
+    ibis: List[Optional[Tuple[np.ndarray, np.ndarray]]] = [None] * P
+    if compute_ibi and alive.any():
+        tr = np.array([k for i in range(P) if alive[i] for k in (2 * i, 2 * i + 1)], dtype=np.int64)
+        bpm = np.array([prior[k // 2] if k % 2 == 0 else 120.0 for k in tr])
+        _, _, _, lag64, beats64, nb64 = eng.tempo_segments_dev(batch.audio, t_off[tr], t_len[tr].astype(np.int32), bpm,
+                                                               _tempo.IBI_HOP_LENGTH, sr)
+        hn = eng.to_host(nb64)
+        mb = int(hn.max()) if len(hn) else 0
+        hb = eng.to_host(beats64[:, : max(mb, 1)])
+        per_track = {}
+        for j, k in enumerate(tr):
+            per_track[int(k)] = _tempo._ibis_from_beats(hb[j, : hn[j]], sr, _tempo.IBI_HOP_LENGTH, _tempo.IBI_MIN_IBIS)
+        for i in range(P):
+            if alive[i]:
+                n_i, s_i = per_track[2 * i], per_track[2 * i + 1]
+                if n_i is not None and len(n_i) >= 4 and s_i is not None and len(s_i) >= 4:
+                    ibis[i] = (n_i, s_i)
+
+    # ---- stage 8: bootstraps, batched per kind
+    q_lo, q_hi = consensus._percentile_args(consensus.CI_LEVEL)
+    valid_t = [(consensus._valid(src_tempos[i]), consensus._valid(nc_tempos[i])) for i in range(P)]
+    valid_p = [(consensus._valid(src_hz[i]), consensus._valid(nc_hz[i])) for i in range(P)]
+    for i in range(P):
+        if alive[i] and (len(valid_t[i][0]) < consensus.MIN_VALID or len(valid_t[i][1]) < consensus.MIN_VALID):
+            failures[i] = consensus._insufficient(*valid_t[i])
+            alive[i] = False
+
+    def boot(jobs):
+        if not jobs:
+            return np.zeros((0, 3))
+        out, _, _ = eng.bootstrap(jobs, consensus.BOOTSTRAP_SEED, consensus.N_BOOTSTRAP, q_lo, q_hi)
+        return out
+
+    t_idx = [i for i in range(P) if alive[i]]
+    t_out = boot([(valid_t[i][1], valid_t[i][0]) for i in t_idx])                 # nc first
+    p_idx = [i for i in t_idx if len(valid_p[i][0]) >= consensus.MIN_VALID and len(valid_p[i][1]) >= consensus.MIN_VALID]
+    p_out = boot([(valid_p[i][1], valid_p[i][0]) for i in p_idx])                 # nc first
+    i_idx = [i for i in t_idx if ibis[i] is not None]
+    i_out = boot([(ibis[i][1], ibis[i][0]) for i in i_idx])                       # src first
+
+    # ---- stage 9: host assembly
+    results: List[Union[consensus.AnalysisResult, Exception]] = [None] * P  # type: ignore[list-item]
+    tmap = {i: t_out[j] for j, i in enumerate(t_idx)}
+    pmap = {i: p_out[j] for j, i in enumerate(p_idx)}
+    imap = {i: i_out[j] for j, i in enumerate(i_idx)}
+    for i in range(P):
+        if failures[i] is not None:
+            results[i] = failures[i]
+            continue
+        ts = (float(tmap[i][0]), (float(tmap[i][1]), float(tmap[i][2])))
+        if i in pmap:
+            ps = (float(pmap[i][0]), (float(pmap[i][1]), float(pmap[i][2])))
+            n_pitch = (len(valid_p[i][0]), len(valid_p[i][1]))
+        else:
+            ps, n_pitch = (1.0, (1.0, 1.0)), (0, 0)
+        res = consensus._assemble(src_hz[i], nc_hz[i], src_tempos[i], nc_tempos[i], valid_t[i][0], valid_t[i][1], ps,
+                                  ts, n_pitch, float(nc_dur[i]), float(src_dur[i]))
+        res.intro_offset_sec = None
+        res.pitch_method = pitch_method
+        if i in imap:
+            res.ibi_ratio = float(imap[i][0])
+            res.ibi_ci = (float(imap[i][1]), float(imap[i][2]))
+        results[i] = res
+    if stats is not None:
+        stats["windows"] = int(len(sel_src) + len(sel_nc))
+        stats["windows_sliced"] = int(len(seg_off))
+        stats["tracks"] = int(n_tracks)
+        stats["d2h_bytes"] = int(eng.d2h_bytes - d2h0)
+        stats["hop64_frames"] = int(sum(1 + int(t_len[k]) // 64 for k in range(n_tracks))) if compute_ibi else 0
+    return results
+
+
+def run_batch_arrays(pairs: Sequence[Tuple[np.ndarray, np.ndarray]], sr: int = SAMPLE_RATE, **kwargs):
+    """[(nc_audio, src_audio), ...] → [AnalysisResult | Exception, ...] (same kwargs as analyse_staged)."""
+    return analyse_staged(stage_pairs(pairs, sr), **kwargs)

@@ -1,0 +1,133 @@
+"""GPU: onset strength / tempo lag / beat DP kernels vs the CPU restatement (oracle/librosa_restated.py).
+
+Tolerances: onset envelope float32, max abs error <= 1e-4 of the envelope's maximum (the FFT
+runs in float32 on the device, in float64 on the oracle); tempo lags and beat frames are
+integers and must be identical when both sides are given the same envelope."""
+import numpy as np
+import pytest
+
+from oracle import librosa_restated as lr
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+SR = 22050
+
+
+def rel_err(a, b):
+    return float(np.max(np.abs(a - b)) / max(1e-12, float(np.max(np.abs(b)))))
+
+
+@pytest.fixture(scope="module")
+def windows():
+    out = []
+    for seed, bpm in ((1, 96.0), (2, 120.0), (3, 139.0)):
+        y = synth.synth(seed, 20.0, SR, bpm=bpm)
+        out += [y[:220500], y[110250:330750]]
+    return out
+
+
+def test_onset_strength_hop512(engine, windows):
+    got = engine.onset_strength(windows, hop=512, sr=SR)
+    for y, g in zip(windows, got):
+        want = lr.onset_strength(y, SR, 512)
+        assert g.shape == want.shape == (431,)
+        assert np.all(g[:3] == 0)
+        assert rel_err(g, want) < 1e-4
+
+
+def test_onset_strength_hop64_and_ragged(engine):
+    ys = [synth.synth(4, 6.0, SR, bpm=110.0), synth.synth(5, 3.3, SR, bpm=128.0)[:70001], np.zeros(5000, np.float32)]
+    got = engine.onset_strength(ys, hop=64, sr=SR)
+    for y, g in zip(ys, got):
+        want = lr.onset_strength(y, SR, 64)
+        assert g.shape == want.shape
+        assert rel_err(g, want) < 1e-4 or float(np.max(np.abs(want))) == 0.0
+    assert np.all(got[2] == 0)
+
+
+def test_onset_top_db_clamp_active(engine):
+    """A window that is silent for its first half exercises the per-segment max − 80 dB floor."""
+    y = synth.synth(6, 10.0, SR, bpm=120.0).copy()
+    y[:110250] *= 1e-6
+    g = engine.onset_strength([y], hop=512, sr=SR)[0]
+    want = lr.onset_strength(y, SR, 512)
+    assert rel_err(g, want) < 1e-4
+
+
+def test_short_segments(engine):
+    for n in (1, 511, 512, 2047, 2049):
+        y = np.random.default_rng(n).standard_normal(n).astype(np.float32)
+        g = engine.onset_strength([y], hop=512, sr=SR)[0]
+        want = lr.onset_strength(y, SR, 512)
+        assert g.shape == want.shape
+        assert np.max(np.abs(g - want)) <= 1e-4 * max(1.0, float(np.max(np.abs(want))))
+
+
+def test_tempo_lag_matches_oracle_on_same_envelope(engine, windows):
+    envs = [lr.onset_strength(y, SR, 512) for y in windows]
+    priors = [120.0, 120.0, 90.0, 150.0, 200.0, 60.0]
+    got = engine.tempo_lags(envs, priors, hop=512, sr=SR)
+    want = [lr.tempo_lag(e, SR, 512, p) for e, p in zip(envs, priors)]
+    assert got.tolist() == want
+
+
+def test_tempo_lag_hop64(engine):
+    y = synth.synth(8, 30.0, SR, bpm=126.0)
+    env = lr.onset_strength(y, SR, 64)
+    got = engine.tempo_lags([env], [120.0], hop=64, sr=SR)
+    assert got.tolist() == [lr.tempo_lag(env, SR, 64, 120.0)]
+
+
+def test_tempo_lag_all_zero_envelope(engine):
+    got = engine.tempo_lags([np.zeros(431, np.float32)], [120.0], hop=512, sr=SR)
+    assert got.tolist() == [0]
+
+
+def test_beat_frames_match_oracle_on_same_envelope(engine, windows):
+    envs = [lr.onset_strength(y, SR, 512) for y in windows]
+    lags = [lr.tempo_lag(e, SR, 512, 120.0) for e in envs]
+    got = engine.beat_frames(envs, lags, hop=512, sr=SR)
+    for e, lag, g in zip(envs, lags, got):
+        bpm = 60.0 * SR / (512 * float(lag))
+        want = lr.beat_track_frames(e, bpm, SR, 512)
+        assert g.tolist() == want.tolist()
+
+
+def test_beat_frames_hop64(engine):
+    y = synth.synth(9, 30.0, SR, bpm=104.0)
+    env = lr.onset_strength(y, SR, 64)
+    lag = lr.tempo_lag(env, SR, 64, 120.0)
+    got = engine.beat_frames([env], [lag], hop=64, sr=SR)[0]
+    want = lr.beat_track_frames(env, 60.0 * SR / (64 * float(lag)), SR, 64)
+    assert got.tolist() == want.tolist()
+
+
+def test_end_to_end_tempo_api(engine, windows):
+    """tempo.batch_estimate_tempo through the drop-in API: the BPM grid value must match the
+    oracle run end-to-end (onset envelopes differ in the last float32 bits, the argmax must not)."""
+    from nightcore_analyzer import io as nio, tempo as ntempo
+    y = synth.synth(12, 40.0, SR, bpm=118.0)
+    wins = nio.slice_windows(y, SR)
+    assert len(wins) == 7
+    lines = []
+    got = ntempo.batch_estimate_tempo(wins, log=lines.append, start_bpm=120.0)
+    assert lines[0] == "    tempo window 1/7  [0.0–10.0 s]" and lines[-1].endswith("windows yielded a confident tempo estimate")
+    for w, g in zip(wins, got):
+        env = lr.onset_strength(w.audio, SR, 512)
+        bpm, beats = lr.beat_track(env, SR, 512, 120.0)
+        want = float(np.atleast_1d(bpm)[0]) if len(beats) >= 4 else None
+        assert g == want
+    assert ntempo.estimate_tempo(wins[2], start_bpm=100.0) is not None
+
+
+def test_estimate_ibis_global(engine):
+    from nightcore_analyzer import tempo as ntempo
+    y = synth.synth(13, 45.0, SR, bpm=125.0)
+    got = ntempo.estimate_ibis_global(y, SR)
+    env = lr.onset_strength(y, SR, 64)
+    _, beats = lr.beat_track(env, SR, 64, 120.0)
+    t = lr.frames_to_time(beats, SR, 64)
+    want = np.diff(t)
+    want = want[want > 0.05]
+    assert got is not None and np.array_equal(got, want)
+    assert ntempo.estimate_ibis_global(np.zeros(22050, np.float32), SR) is None
