@@ -1,0 +1,98 @@
+// Shared STFT core: one warp turns one 2048-sample frame (already in shared memory) into its
+// 1025-bin power spectrum (periodic Hann, real FFT as a packed 1024-point complex FFT).
+// Used by the onset front-end (stft_onset.cu) and the tuning estimator (chroma.cu).
+#pragma once
+#include "ncfa_common.cuh"
+#include "fft_core.cuh"
+
+namespace ncfa {
+
+constexpr int kScrStride = 33;  // complex elements per row of the per-warp transpose tile
+
+// a · W_64^K2,  W_64 = exp(-2πi/64), K2 < 32
+template <int K2>
+__device__ __forceinline__ cf mul_w64(cf a) {
+    constexpr float C[32] = {
+        1.00000000000000000000f,  0.99518472667219692873f,  0.98078528040323043058f,  0.95694033573220882438f,
+        0.92387953251128673848f,  0.88192126434835504956f,  0.83146961230254523567f,  0.77301045336273699338f,
+        0.70710678118654757274f,  0.63439328416364548779f,  0.55557023301960228867f,  0.47139673682599780857f,
+        0.38268343236508983729f,  0.29028467725446233105f,  0.19509032201612833135f,  0.09801714032956077016f,
+        0.0f,                     -0.09801714032956064526f, -0.19509032201612819257f, -0.29028467725446216452f,
+        -0.38268343236508972627f, -0.47139673682599769755f, -0.55557023301960195560f, -0.63439328416364537677f,
+        -0.70710678118654746172f, -0.77301045336273699338f, -0.83146961230254534669f, -0.88192126434835493853f,
+        -0.92387953251128673848f, -0.95694033573220882438f, -0.98078528040323043058f, -0.99518472667219681771f};
+    constexpr float S[32] = {
+        0.0f,                    0.09801714032956060363f, 0.19509032201612824808f, 0.29028467725446233105f,
+        0.38268343236508978178f, 0.47139673682599764204f, 0.55557023301960217765f, 0.63439328416364548779f,
+        0.70710678118654746172f, 0.77301045336273699338f, 0.83146961230254523567f, 0.88192126434835493853f,
+        0.92387953251128673848f, 0.95694033573220893540f, 0.98078528040323043058f, 0.99518472667219681771f,
+        1.0f,                    0.99518472667219692873f, 0.98078528040323043058f, 0.95694033573220893540f,
+        0.92387953251128673848f, 0.88192126434835504956f, 0.83146961230254545772f, 0.77301045336273710440f,
+        0.70710678118654757274f, 0.63439328416364548779f, 0.55557023301960217765f, 0.47139673682599786408f,
+        0.38268343236508989280f, 0.29028467725446238656f, 0.19509032201612860891f, 0.09801714032956082567f};
+    if constexpr (K2 == 0) {
+        return a;
+    } else {
+        // a · (c - i s)
+        return cf{a.x * C[K2] + a.y * S[K2], a.y * C[K2] - a.x * S[K2]};
+    }
+}
+
+template <int K2>
+struct PostStage {
+    // un-pack bin k = lane + 32·K2 of the real FFT and store its power
+    static __device__ __forceinline__ void run(const cf (&v)[32], int lane, cf twl, float *pw) {
+        cf zk = v[br5(K2)];
+        cf own = v[br5((32 - K2) & 31)];
+        cf snd = v[br5(31 - K2)];
+        int src = (32 - lane) & 31;
+        cf p;
+        p.x = __shfl_sync(0xffffffffu, snd.x, src);
+        p.y = __shfl_sync(0xffffffffu, snd.y, src);
+        if (lane == 0) p = own;
+        cf e = cf{0.5f * (zk.x + p.x), 0.5f * (zk.y - p.y)};
+        cf o = cf{0.5f * (zk.y + p.y), -0.5f * (zk.x - p.x)};
+        cf w = mul_w64<K2>(twl);  // W_2048^(lane + 32·K2)
+        cf wo = cmul(w, o);
+        cf x = cadd(e, wo);
+        pw[lane + 32 * K2] = x.x * x.x + x.y * x.y;
+        if (K2 == 0 && lane == 0) {
+            float ny = e.x - o.x;  // bin 1024
+            pw[1024] = ny * ny;
+        }
+        if constexpr (K2 + 1 < 32) PostStage<K2 + 1>::run(v, lane, twl, pw);
+    }
+};
+
+
+// fr: 2048 samples (shared), hann: 2048 (shared), tw: [32][32] W_1024 twiddles (shared),
+// scr: per-warp scratch of 32*kScrStride float2; on return its first 1025 floats hold |X[k]|^2.
+__device__ __forceinline__ void warp_power_spectrum(const float *fr, const float *hann, const float2 *tw, float2 *scr,
+                                                    cf twl, int lane) {
+    cf v[32];
+#pragma unroll
+    for (int n1 = 0; n1 < 32; ++n1) {
+        float2 xs = *reinterpret_cast<const float2 *>(fr + 64 * n1 + 2 * lane);
+        float2 ws = *reinterpret_cast<const float2 *>(hann + 64 * n1 + 2 * lane);
+        v[n1] = cf{xs.x * ws.x, xs.y * ws.y};
+    }
+    fft32_dif(v);
+#pragma unroll
+    for (int k1 = 0; k1 < 32; ++k1) {
+        float2 t = tw[k1 * 32 + lane];
+        cf y = cmul(v[br5(k1)], cf{t.x, t.y});
+        scr[k1 * kScrStride + lane] = make_float2(y.x, y.y);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int n2 = 0; n2 < 32; ++n2) {
+        float2 t = scr[lane * kScrStride + n2];
+        v[n2] = cf{t.x, t.y};
+    }
+    __syncwarp();
+    fft32_dif(v);
+    PostStage<0>::run(v, lane, twl, reinterpret_cast<float *>(scr));
+    __syncwarp();
+}
+
+}  // namespace ncfa
