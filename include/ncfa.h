@@ -107,6 +107,64 @@ int ncfa_bootstrap_ratio_batched(const double *d_a, const int64_t *d_a_off, cons
                                  double q_hi, double *d_out, double *d_boot, int32_t *d_idx, void *d_workspace,
                                  size_t workspace_bytes, void *stream);
 
+/* ---- pitch.py:55-64 _mean_chroma → librosa.feature.chroma_cqt(y, sr, bins_per_octave=36, hop_length=512).mean(axis=1)
+ * Step 1 (librosa.estimate_tuning inside cqt): STFT(2048, 512) magnitudes → piptrack peaks in
+ * 150..4000 Hz → peaks at or above the segment's median magnitude → 100-bin histogram of the
+ * 1/36-octave residual → d_tuning_idx[i] = first fullest bin j; tuning = −0.5 + j/100 (50 when the
+ * segment has no peak, i.e. tuning 0.0). */
+size_t ncfa_tuning_workspace_bytes(int n_seg, int max_seg_len);
+int ncfa_tuning_estimate_batched(const float *d_audio, const int64_t *d_seg_off, const int32_t *d_seg_len, int n_seg,
+                                 int max_seg_len, int sr, int32_t *d_tuning_idx, void *d_workspace,
+                                 size_t workspace_bytes, void *stream);
+
+/* Step 2: 7-octave, 36-bins/octave CQT from C1·2^(tuning/36) (rectangular 1024-sample frames, hop
+ * 512 >> octave, 2:1 half-band decimation ×√2 between octaves, 1 %-sparsified FFT basis folded with
+ * the DFT into one real 72×1024 matrix per tuning), |·|, fold to 12 chroma (3 bins per semitone,
+ * rolled −1), inf-norm per frame, mean over frames → d_chroma[12·i .. 12·i+11] (float64).
+ * sr must be 22050 (the layout the reference always uses: io.SAMPLE_RATE, io.py:19). */
+size_t ncfa_chroma_workspace_bytes(int n_seg, int max_seg_len);
+int ncfa_chroma_mean_batched(const float *d_audio, const int64_t *d_seg_off, const int32_t *d_seg_len, int n_seg,
+                             int max_seg_len, int sr, const int32_t *d_tuning_idx, double *d_chroma,
+                             void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* ---- pitch.py:67-85 _cyclic_xcorr_peak: d_lag[p] = first argmax_k dot(src_p, roll(nc_p, −k)),
+ * wrapped to (−n_bins/2, n_bins/2]; d_src / d_nc hold n_pairs vectors of n_bins float64. */
+int ncfa_cyclic_xcorr_batched(const double *d_src, const double *d_nc, int n_pairs, int n_bins, int32_t *d_lag,
+                              void *stream);
+
+/* ---- xcorr.py:113-148 candidate search of estimate_speed_xcorr.  Reference window w is
+ * d_a[d_a_pos[w] .. +win); its candidates are d_b[d_b_lo[w] + j·stride .. +win), j < d_n_cand[w]
+ * (the host applies xcorr.py:95-111,121-125 to produce these tables).  c = dot/(‖wa‖‖wb‖) with the
+ * reference's float32 roundings of dot and norms; d_best_j[w] = first j with the largest c when it
+ * is > 0 and the window passes the RMS gate (xcorr.py:118) and the 1e-10 norm gates, else −1;
+ * d_best_c[w] = that c (0 when none). */
+size_t ncfa_xcorr_workspace_bytes(int n_windows, int max_cand);
+int ncfa_xcorr_search_batched(const float *d_a, const float *d_b, const int64_t *d_a_pos, const int64_t *d_b_lo,
+                              const int32_t *d_n_cand, int n_windows, int max_cand, int win, int stride,
+                              double rms_gate, int32_t *d_best_j, double *d_best_c, void *d_workspace,
+                              size_t workspace_bytes, void *stream);
+
+/* ---- xcorr.py:165-259 find_content_offset (pipeline.run(auto_align=True)) -----------------------
+ * ncfa_decimate2: librosa.resample(orig_sr = 2·target_sr) stand-in — 127-tap Kaiser half-band, no
+ *   scaling, n_out = ceil(n_in/2) (soxr_hq is not reproducible; documented deviation).
+ * ncfa_f32_to_f64: the .astype(np.float64) of the RMS envelopes (xcorr.py:210-211).
+ * ncfa_align_search: for each candidate speed s: stretched = np.interp(linspace(0,1,n_stretched[s]),
+ *   linspace(0,1,n_nc), nc_env); corr = np.correlate(src_env, stretched, 'valid')[:n_lags[s]];
+ *   d_peak_idx[s] = first argmax; d_score[s] = corr[peak]/sqrt(Σ src_env[peak:peak+n]²·Σ stretched²)
+ *   (0 when the denominator is <= 1e-12).  n_lags[s] <= 0 marks a speed the reference skips. */
+int ncfa_decimate2(const float *d_in, int64_t n_in, float *d_out, void *stream);
+int ncfa_f32_to_f64(const float *d_in, int64_t n, double *d_out, void *stream);
+size_t ncfa_align_workspace_bytes(int n_speeds, int max_stretched, int max_lags);
+int ncfa_align_search(const double *d_src_env, int n_src, const double *d_nc_env, int n_nc,
+                      const int32_t *d_n_stretched, const int32_t *d_n_lags, int n_speeds, int max_stretched,
+                      int max_lags, int32_t *d_peak_idx, double *d_score, void *d_workspace, size_t workspace_bytes,
+                      void *stream);
+
+/* Host-side constant-table builders (no GPU needed; used by the CPU test-suite):
+ * h_K[1024][72] = the CQT contraction matrix of tuning index j; h_taps[127] = the half-band FIR. */
+int ncfa_host_cqt_matrix(int sr, int tuning_index, float *h_K);
+int ncfa_host_halfband_taps(double *h_taps);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,793 @@
+// CQT chroma family.  Replaces librosa.feature.chroma_cqt(y, sr, bins_per_octave=36, hop_length=512)
+// followed by .mean(axis=1) as called by pitch._mean_chroma (pitch.py:55-64), and the 12-lag cyclic
+// cross-correlation of pitch._cyclic_xcorr_peak (pitch.py:67-85).  SURVEY.md §3.4, Appendix A.8.
+//
+//   tuning_peaks_kernel   STFT(2048, 512, Hann) magnitude → piptrack peaks (parabolic interpolation)
+//                         in 150..4000 Hz → (magnitude, 1/36-octave residual histogram bin) per peak
+//   tuning_pick_kernel    median magnitude over the segment (radix select) → histogram of the peaks at
+//                         or above it → first fullest bin = tuning index j, tuning = −0.5 + j/100
+//   decimate2_kernel      2:1 decimation ×√2 between octaves (127-tap Kaiser half-band, float64 sums)
+//   cqt_chroma_kernel     per octave: the 36 CQT responses of every frame as ONE real contraction
+//                         C[72 × frames] = K[72 × 1024] · X[1024 × frames],  X[n][t] = y_oct[t·hop_oct + n − 512]
+//                         (K = sparsified FFT-domain basis ∘ DFT, folded on the host in float64 — the same
+//                         linear map as rectangular-window STFT followed by the sparse basis product),
+//                         then |·|, fold 252 → 12 chroma, inf-norm per frame, partial sums over frames
+//   chroma_mean_kernel    partial sums → mean chroma float64[12] per segment
+//   cyclic_xcorr_kernel   argmax_k dot(src, roll(nc, −k)) wrapped to (−n/2, n/2]
+#include <cmath>
+#include <algorithm>
+#include <complex>
+#include <map>
+#include <mutex>
+#include <vector>
+#include "stft_core.cuh"
+
+namespace ncfa {
+
+constexpr int kNTunings = 100;
+constexpr int kCqtBins = 36;          // bins per octave
+constexpr int kCqtRows = 2 * kCqtBins;  // real + imaginary rows of K
+constexpr int kCqtNfft = 1024;
+constexpr int kOctaves = 7;
+constexpr int kChroma = 12;
+constexpr int kHbTaps = 127;
+constexpr int kPeakStride = 180;  // ≥ max local maxima among the 358 candidate bins (179)
+
+struct ChromaTables {
+    const float *K;     // [100][1024][72]  K[j][n][r]: r < 36 real part of bin r, r ≥ 36 imaginary part of bin r−36
+    const double *hb;   // [127] half-band taps
+};
+
+// ------------------------------------------------------------------------------------------------ host tables
+static void fft_inplace(std::vector<std::complex<double>> &a) {
+    const size_t n = a.size();
+    for (size_t i = 1, j = 0; i < n; ++i) {
+        size_t bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) std::swap(a[i], a[j]);
+    }
+    const double PI = 3.14159265358979323846;
+    for (size_t len = 2; len <= n; len <<= 1) {
+        const double ang = -2.0 * PI / (double)len;
+        for (size_t i = 0; i < n; i += len)
+            for (size_t k = 0; k < len / 2; ++k) {
+                const std::complex<double> w(cos(ang * (double)k), sin(ang * (double)k));
+                const std::complex<double> u = a[i + k], v = a[i + k + len / 2] * w;
+                a[i + k] = u + v;
+                a[i + k + len / 2] = u - v;
+            }
+    }
+}
+
+// librosa.filters.wavelet + __vqt_filter_fft + util.sparsify_rows for the top octave at the full rate
+// (Appendix A.8), then folded with the DFT and the final 1/sqrt(length) scale:  K[n][r]
+static int build_cqt_matrix(int sr, double tuning, std::vector<float> &K /* [1024][72] */) {
+    const double PI = 3.14159265358979323846;
+    const double c1 = 440.0 * pow(2.0, (12.0 * 2.0 + 0.0 - 69.0) / 12.0);
+    const double fmin = c1 * pow(2.0, tuning / 36.0);
+    const double r = pow(2.0, 1.0 / 36.0);
+    const double alpha = (r * r - 1.0) / (r * r + 1.0);
+    const double Q = 1.0 / alpha;
+    const int n_bins = kOctaves * kCqtBins;
+    std::vector<std::complex<double>> tw(kCqtNfft);
+    for (int i = 0; i < kCqtNfft; ++i) tw[i] = std::complex<double>(cos(-2.0 * PI * i / kCqtNfft), sin(-2.0 * PI * i / kCqtNfft));
+    K.assign((size_t)kCqtNfft * kCqtRows, 0.0f);
+    for (int b = 0; b < kCqtBins; ++b) {
+        const int k = n_bins - kCqtBins + b;
+        const double freq = fmin * pow(2.0, (double)k / 36.0);
+        const double ilen = Q * (double)sr / freq;
+        const long t0 = (long)floor(-ilen / 2.0), t1 = (long)floor(ilen / 2.0);
+        const int N = (int)(t1 - t0);
+        if (N < 2 || N > kCqtNfft) {
+            set_error("CQT filter length %d does not fit n_fft=1024 at sr=%d", N, sr);
+            return NCFA_E_INVALID;
+        }
+        std::vector<std::complex<double>> sig(N);
+        double l1 = 0.0;
+        for (int i = 0; i < N; ++i) {
+            const double t = (double)(t0 + i);
+            const double ph = t * 2.0 * PI * freq / (double)sr;
+            const double w = 0.5 - 0.5 * cos(2.0 * PI * (double)i / (double)N);
+            sig[i] = std::complex<double>(cos(ph), sin(ph)) * w;
+            l1 += std::abs(sig[i]);
+        }
+        std::vector<std::complex<double>> buf(kCqtNfft, std::complex<double>(0.0, 0.0));
+        const int lpad = (kCqtNfft - N) / 2;
+        for (int i = 0; i < N; ++i) buf[lpad + i] = sig[i] / l1 * (ilen / (double)kCqtNfft);
+        fft_inplace(buf);
+        // sparsify_rows(quantile=0.01) over the 513 kept bins
+        const int nb = kCqtNfft / 2 + 1;
+        std::vector<double> mags(nb), sorted;
+        double norm = 0.0;
+        for (int i = 0; i < nb; ++i) {
+            mags[i] = std::abs(buf[i]);
+            norm += mags[i];
+        }
+        sorted = mags;
+        std::sort(sorted.begin(), sorted.end());
+        double cum = 0.0, thr = sorted[0];
+        for (int i = 0; i < nb; ++i) {
+            cum += sorted[i] / norm;
+            if (!(cum < 0.01)) {
+                thr = sorted[i];
+                break;
+            }
+        }
+        const double scale = 1.0 / sqrt(ilen);  // V /= sqrt(lengths): identical in every octave (length·2^oct vs sqrt(2^oct)·√2 chain)
+        std::vector<double> kre(kCqtNfft, 0.0), kim(kCqtNfft, 0.0);
+        for (int i = 0; i < nb; ++i) {
+            if (!(mags[i] >= thr)) continue;
+            const std::complex<double> c((double)(float)buf[i].real(), (double)(float)buf[i].imag());  // complex64 basis
+            for (int n = 0; n < kCqtNfft; ++n) {
+                const std::complex<double> v = c * tw[(i * n) & (kCqtNfft - 1)];
+                kre[n] += v.real();
+                kim[n] += v.imag();
+            }
+        }
+        for (int n = 0; n < kCqtNfft; ++n) {
+            K[(size_t)n * kCqtRows + b] = (float)(kre[n] * scale);
+            K[(size_t)n * kCqtRows + kCqtBins + b] = (float)(kim[n] * scale);
+        }
+    }
+    return NCFA_OK;
+}
+
+static double bessel_i0(double x) {  // power series, converges fast for x ≤ ~20
+    const double q = x * x / 4.0;
+    double term = 1.0, sum = 1.0;
+    for (int k = 1; k < 200; ++k) {
+        term *= q / ((double)k * (double)k);
+        sum += term;
+        if (term < 1e-18 * sum) break;
+    }
+    return sum;
+}
+
+static void build_halfband(std::vector<double> &h) {
+    // Kaiser(127, β=10)-windowed sinc half-band, DC gain 1 (the 2:1 decimator between CQT octaves; librosa
+    // uses soxr_hq there, which is not reproducible — documented deviation)
+    const double PI = 3.14159265358979323846;
+    h.assign(kHbTaps, 0.0);
+    double hs = 0.0;
+    const double al = (kHbTaps - 1) / 2.0, i0b = bessel_i0(10.0);
+    for (int i = 0; i < kHbTaps; ++i) {
+        const double n = (double)i - al;
+        double x = 0.5 * n;
+        if (x == 0.0) x = 1e-20;
+        const double sinc = sin(PI * x) / (PI * x);
+        const double rr = n / al;
+        const double kw = bessel_i0(10.0 * sqrt(fmax(0.0, 1.0 - rr * rr))) / i0b;
+        h[i] = 0.5 * sinc * kw;
+        hs += h[i];
+    }
+    for (auto &v : h) v /= hs;
+}
+
+static std::mutex g_hb_mu;
+static std::map<int, const double *> g_hb;
+int get_halfband_device(const double **out) {
+    int dev = 0;
+    NCFA_CUDA_OK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_hb_mu);
+    auto it = g_hb.find(dev);
+    if (it != g_hb.end()) {
+        *out = it->second;
+        return NCFA_OK;
+    }
+    std::vector<double> h;
+    build_halfband(h);
+    double *dh = nullptr;
+    NCFA_CUDA_OK(cudaMalloc(&dh, h.size() * sizeof(double)));
+    NCFA_CUDA_OK(cudaMemcpy(dh, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+    g_hb[dev] = dh;
+    *out = dh;
+    return NCFA_OK;
+}
+
+static std::mutex g_chroma_mu;
+static std::map<std::pair<int, int>, ChromaTables> g_chroma_tables;
+
+static int get_chroma_tables(int sr, ChromaTables *out) {
+    int dev = 0;
+    NCFA_CUDA_OK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_chroma_mu);
+    auto key = std::make_pair(dev, sr);
+    auto it = g_chroma_tables.find(key);
+    if (it != g_chroma_tables.end()) {
+        *out = it->second;
+        return NCFA_OK;
+    }
+    std::vector<float> all((size_t)kNTunings * kCqtNfft * kCqtRows), one;
+    for (int j = 0; j < kNTunings; ++j) {
+        const double tuning = (double)j * 0.01 + (-0.5);  // np.linspace(-0.5, 0.5, 101)[j]
+        int rc = build_cqt_matrix(sr, tuning, one);
+        if (rc) return rc;
+        memcpy(all.data() + (size_t)j * kCqtNfft * kCqtRows, one.data(), one.size() * sizeof(float));
+    }
+    ChromaTables t;
+    float *dK = nullptr;
+    NCFA_CUDA_OK(cudaMalloc(&dK, all.size() * sizeof(float)));
+    NCFA_CUDA_OK(cudaMemcpy(dK, all.data(), all.size() * sizeof(float), cudaMemcpyHostToDevice));
+    {
+        int rc = get_halfband_device(&t.hb);
+        if (rc) return rc;
+    }
+    t.K = dK;
+    g_chroma_tables[key] = t;
+    *out = t;
+    return NCFA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ geometry
+// octave o works on level o of the decimation pyramid: len_0 = n, len_o = ceil(len_{o-1}/2), hop_o = 512 >> o
+__host__ __device__ inline int level_len(int n, int o) {
+    for (int i = 0; i < o; ++i) n = (n + 1) >> 1;
+    return n;
+}
+__host__ __device__ inline int cqt_frames(int n) {  // cqt trims every octave to the shortest (max_col)
+    int f = 0x7fffffff;
+    for (int o = 0; o < kOctaves; ++o) {
+        const int fo = 1 + level_len(n, o) / (512 >> o);
+        f = fo < f ? fo : f;
+    }
+    return f;
+}
+// float offsets of pyramid levels 1..6 of one segment (each 4-aligned), total in off[7]
+__host__ __device__ inline void pyramid_layout(int max_len, size_t off[kOctaves + 1]) {
+    size_t p = 0;
+    off[0] = 0;
+    for (int o = 1; o < kOctaves; ++o) {
+        off[o] = p;
+        p += ((size_t)level_len(max_len, o) + 3) / 4 * 4;
+    }
+    off[kOctaves] = p;
+}
+
+// ------------------------------------------------------------------------------------------------ tuning
+constexpr int kTunWarps = 4;
+constexpr int kTunThreads = kTunWarps * 32;
+constexpr int kTunFramesPerTile = 8;
+constexpr int kTunTile = (kTunFramesPerTile - 1) * 512 + 2048;
+
+struct TuningSmem {
+    float tile[kTunTile];
+    float hann[2048];
+    float2 tw[1024];
+    float2 scr[kTunWarps][32 * kScrStride];
+};
+
+__global__ void __launch_bounds__(kTunThreads) tuning_peaks_kernel(const float *__restrict__ audio,
+                                                                   const int64_t *__restrict__ seg_off,
+                                                                   const int32_t *__restrict__ seg_len, int frame_stride,
+                                                                   int kmin, int kmax, double hz_per_bin, Tables tb,
+                                                                   float *__restrict__ pk_mag,
+                                                                   uint8_t *__restrict__ pk_bin,
+                                                                   int32_t *__restrict__ pk_cnt) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TuningSmem &sm = *reinterpret_cast<TuningSmem *>(smem_raw);
+    const int seg = blockIdx.y;
+    const int len = seg_len[seg];
+    const int n_frames = 1 + len / 512;
+    const int f0 = blockIdx.x * kTunFramesPerTile;
+    if (f0 >= n_frames) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *src = audio + seg_off[seg];
+    for (int i = tid; i < 2048; i += kTunThreads) sm.hann[i] = tb.hann[i];
+    for (int i = tid; i < 1024; i += kTunThreads) sm.tw[i] = tb.tw1024[i];
+    const int nf_tile = min(kTunFramesPerTile, n_frames - f0);
+    const int tile_n = (nf_tile - 1) * 512 + 2048;
+    const int64_t pos0 = (int64_t)f0 * 512 - 1024;
+    for (int i = tid; i < tile_n; i += kTunThreads) {
+        const int64_t p = pos0 + i;
+        sm.tile[i] = (p >= 0 && p < len) ? __ldg(src + p) : 0.0f;
+    }
+    __syncthreads();
+    const cf twl = cf{tb.tw2048[lane].x, tb.tw2048[lane].y};
+    float2 *scr = sm.scr[warp];
+    float *S = reinterpret_cast<float *>(scr);
+    for (int fl = warp; fl < nf_tile; fl += kTunWarps) {
+        warp_power_spectrum(sm.tile + fl * 512, sm.hann, sm.tw, scr, twl, lane);
+        float mx = 0.0f;
+        for (int k = lane; k < 1025; k += 32) {
+            const float m = sqrtf(S[k]);
+            S[k] = m;
+            mx = fmaxf(mx, m);
+        }
+        mx = warp_max(mx);
+        __syncwarp();
+        const float ref = 0.1f * mx;  // threshold · max over the frame
+        const size_t slot0 = ((size_t)seg * frame_stride + (f0 + fl)) * kPeakStride;
+        int count = 0;
+        for (int kb = kmin; kb <= kmax; kb += 32) {
+            const int k = kb + lane;
+            bool peak = false;
+            float mag = 0.0f;
+            int hbin = 0;
+            if (k <= kmax) {
+                const float sl = S[k - 1], sc = S[k], sr_ = S[k + 1];
+                const float ml = sl > ref ? sl : 0.0f, mc = sc > ref ? sc : 0.0f, mr = sr_ > ref ? sr_ : 0.0f;
+                peak = (mc > ml) && (mc >= mr);
+                if (peak) {
+                    const float a = __fsub_rn(__fadd_rn(sr_, sl), __fmul_rn(2.0f, sc));
+                    const float b = __fmul_rn(__fsub_rn(sr_, sl), 0.5f);
+                    const float shift = (fabsf(b) >= fabsf(a)) ? 0.0f : __fdiv_rn(-b, a);
+                    mag = __fadd_rn(sc, __fmul_rn(__fmul_rn(0.5f, b), shift));
+                    const double pitch = __dmul_rn(__dadd_rn((double)k, (double)shift), hz_per_bin);
+                    double res = fmod(__dmul_rn(36.0, log2(pitch / 27.5)), 1.0);
+                    if (res >= 0.5) res = __dadd_rn(res, -1.0);
+                    int i0 = (int)floor((res + 0.5) * 100.0);
+                    i0 = i0 < 0 ? 0 : (i0 > 99 ? 99 : i0);
+                    // bin i holds edge(i) <= x < edge(i+1), edge(i) = i·0.01 − 0.5 as np.linspace computes it
+                    while (i0 > 0 && res < __dadd_rn(__dmul_rn((double)i0, 0.01), -0.5)) --i0;
+                    while (i0 < 99 && res >= __dadd_rn(__dmul_rn((double)(i0 + 1), 0.01), -0.5)) ++i0;
+                    hbin = i0;
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, peak);
+            if (peak) {
+                const int slot = count + __popc(m & ((1u << lane) - 1u));
+                pk_mag[slot0 + slot] = mag;
+                pk_bin[slot0 + slot] = (uint8_t)hbin;
+            }
+            count += __popc(m);
+        }
+        if (lane == 0) pk_cnt[(size_t)seg * frame_stride + f0 + fl] = count;
+        __syncwarp();
+    }
+}
+
+// median(mag) over all peaks of the segment, histogram of residual bins of peaks with mag >= median
+__global__ void __launch_bounds__(256) tuning_pick_kernel(const int32_t *__restrict__ seg_len, int frame_stride,
+                                                          const float *__restrict__ pk_mag,
+                                                          const uint8_t *__restrict__ pk_bin,
+                                                          const int32_t *__restrict__ pk_cnt,
+                                                          int32_t *__restrict__ tuning_idx) {
+    __shared__ int hist[256];
+    __shared__ unsigned s_prefix;
+    __shared__ int s_rank, s_total;
+    __shared__ float s_sel[2];
+    const int seg = blockIdx.x;
+    const int n_frames = 1 + seg_len[seg] / 512;
+    const int tid = threadIdx.x;
+    const int32_t *cnt = pk_cnt + (size_t)seg * frame_stride;
+    const float *mags = pk_mag + (size_t)seg * frame_stride * kPeakStride;
+    const uint8_t *bins = pk_bin + (size_t)seg * frame_stride * kPeakStride;
+    if (tid == 0) s_total = 0;
+    __syncthreads();
+    int local = 0;
+    for (int f = tid; f < n_frames; f += 256) local += cnt[f];
+    atomicAdd(&s_total, local);
+    __syncthreads();
+    const int total = s_total;
+    if (total == 0) {
+        if (tid == 0) tuning_idx[seg] = 50;  // pitch_tuning: no pitches → 0.0 = edge 50
+        return;
+    }
+    // one warp walks one frame's slots at a time
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int which = 0; which < 2; ++which) {
+        if (tid == 0) {
+            s_prefix = 0u;
+            s_rank = which == 0 ? (total - 1) / 2 : total / 2;
+        }
+        __syncthreads();
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            hist[tid] = 0;
+            __syncthreads();
+            const unsigned prefix = s_prefix;
+            const unsigned himask = (shift == 24) ? 0u : (~0u << (shift + 8));
+            for (int f = warp; f < n_frames; f += 8) {
+                const int c = cnt[f];
+                for (int e = lane; e < c; e += 32) {
+                    const unsigned key = float_to_ordered(mags[(size_t)f * kPeakStride + e]);
+                    if ((key & himask) == prefix) atomicAdd(&hist[(key >> shift) & 0xff], 1);
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int r = s_rank, b = 0;
+                while (b < 255 && r >= hist[b]) {
+                    r -= hist[b];
+                    ++b;
+                }
+                s_rank = r;
+                s_prefix = prefix | ((unsigned)b << shift);
+            }
+            __syncthreads();
+        }
+        if (tid == 0) s_sel[which] = ordered_to_float(s_prefix);
+        __syncthreads();
+    }
+    const float thr = __fmul_rn(__fadd_rn(s_sel[0], s_sel[1]), 0.5f);  // np.median of float32
+    hist[tid] = 0;
+    __syncthreads();
+    for (int f = warp; f < n_frames; f += 8) {
+        const int c = cnt[f];
+        for (int e = lane; e < c; e += 32)
+            if (mags[(size_t)f * kPeakStride + e] >= thr) atomicAdd(&hist[bins[(size_t)f * kPeakStride + e]], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int best = 0;
+        for (int i = 1; i < kNTunings; ++i)
+            if (hist[i] > hist[best]) best = i;  // np.argmax: first maximum
+        tuning_idx[seg] = best;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ decimation
+// out[i] = float32( √2 · Σ_k h[k]·in[2i + k − 63] ),  n_out = ceil(n_in / 2)
+__global__ void __launch_bounds__(256) decimate2_kernel(const float *__restrict__ audio,
+                                                        const int64_t *__restrict__ seg_off,
+                                                        const int32_t *__restrict__ seg_len, int level,
+                                                        float *__restrict__ pyr, size_t pyr_stride, size_t in_off,
+                                                        size_t out_off, const double *__restrict__ hb) {
+    __shared__ double h[kHbTaps];
+    __shared__ float xin[2 * 256 + kHbTaps - 1];
+    const int seg = blockIdx.y;
+    const int n0 = seg_len[seg];
+    const int n_in = level_len(n0, level - 1), n_out = (n_in + 1) >> 1;
+    const int i0 = blockIdx.x * 256;
+    if (i0 >= n_out) return;
+    const float *in = (level == 1) ? audio + seg_off[seg] : pyr + (size_t)seg * pyr_stride + in_off;
+    float *out = pyr + (size_t)seg * pyr_stride + out_off;
+    for (int i = threadIdx.x; i < kHbTaps; i += 256) h[i] = hb[i];
+    const int base = 2 * i0 - (kHbTaps - 1) / 2;
+    for (int i = threadIdx.x; i < 2 * 256 + kHbTaps - 1; i += 256) {
+        const int p = base + i;
+        xin[i] = (p >= 0 && p < n_in) ? __ldg(in + p) : 0.0f;
+    }
+    __syncthreads();
+    const int i = i0 + threadIdx.x;
+    if (i >= n_out) return;
+    double acc = 0.0;
+#pragma unroll 8
+    for (int k = 0; k < kHbTaps; ++k) acc = fma(h[k], (double)xin[2 * threadIdx.x + k], acc);
+    out[i] = (float)(acc * 1.4142135623730951);
+}
+
+// ------------------------------------------------------------------------------------------------ CQT → chroma
+constexpr int kCqtTF = 32;                                   // frames per CTA
+constexpr int kCqtKT = 32;                                   // n (time-sample) tile of the contraction
+constexpr int kCqtThreads = 160;                             // 18 row groups × 8 frame groups = 144 active
+constexpr int kCqtSpanMax = (kCqtTF - 1) * 512 + kCqtNfft;   // widest sample span (octave 0)
+
+struct CqtSmem {
+    float sig[kCqtSpanMax + kCqtTF + kCqtNfft / 8 + 8];  // skewed: sample s lives at s + (s >> log2 hop)
+    float kt[kCqtKT][kCqtRows];                          // K tile, n-major
+    float c[kCqtRows][kCqtTF + 1];                       // responses of the current octave
+    float chroma[kChroma][kCqtTF];                       // summed over octaves
+};
+
+template <int L2HOP>
+__device__ __forceinline__ void cqt_octave(CqtSmem &sm, const float *__restrict__ y, int len, int t0,
+                                           const float *__restrict__ Kj, int tid) {
+    constexpr int HOP = 1 << L2HOP;
+    constexpr int SPAN = (kCqtTF - 1) * HOP + kCqtNfft;
+    // ---- stage the sample span of this octave (centred frames: frame t starts at t·hop − 512)
+    const int64_t pos0 = (int64_t)t0 * HOP - kCqtNfft / 2;
+    for (int s = tid; s < SPAN; s += kCqtThreads) {
+        const int64_t p = pos0 + s;
+        sm.sig[s + (s >> L2HOP)] = (p >= 0 && p < len) ? __ldg(y + p) : 0.0f;
+    }
+    const int ty = tid >> 3, tx = tid & 7;  // rows 4ty..4ty+3, frames tx + 8c
+    const bool active = ty < kCqtRows / 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    int fbase[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) fbase[c] = (tx + 8 * c) * (HOP + 1);
+    // register prefetch of the K tile: 32×72 floats = 576 float4, ≤ 4 per thread
+    constexpr int kT4 = kCqtKT * kCqtRows / 4;
+    float4 pre[4];
+    const float4 *Kg = reinterpret_cast<const float4 *>(Kj);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int idx = tid + q * kCqtThreads;
+        pre[q] = idx < kT4 ? __ldg(Kg + idx) : make_float4(0, 0, 0, 0);
+    }
+    for (int n0 = 0; n0 < kCqtNfft; n0 += kCqtKT) {
+        __syncthreads();  // previous tile consumed (and, first time, the span is staged)
+        float4 *kt4 = reinterpret_cast<float4 *>(&sm.kt[0][0]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int idx = tid + q * kCqtThreads;
+            if (idx < kT4) kt4[idx] = pre[q];
+        }
+        __syncthreads();
+        if (n0 + kCqtKT < kCqtNfft) {
+            const float4 *Kn = Kg + (size_t)(n0 + kCqtKT) * kCqtRows / 4;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int idx = tid + q * kCqtThreads;
+                pre[q] = idx < kT4 ? __ldg(Kn + idx) : make_float4(0, 0, 0, 0);
+            }
+        }
+        if (active) {
+#pragma unroll
+            for (int nn = 0; nn < kCqtKT; ++nn) {
+                const int n = n0 + nn;
+                const float4 kv = *reinterpret_cast<const float4 *>(&sm.kt[nn][4 * ty]);
+                const int o = n + (n >> L2HOP);
+                float x[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) x[c] = sm.sig[fbase[c] + o];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    acc[0][c] = fmaf(kv.x, x[c], acc[0][c]);
+                    acc[1][c] = fmaf(kv.y, x[c], acc[1][c]);
+                    acc[2][c] = fmaf(kv.z, x[c], acc[2][c]);
+                    acc[3][c] = fmaf(kv.w, x[c], acc[3][c]);
+                }
+            }
+        }
+    }
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) sm.c[4 * ty + i][tx + 8 * c] = acc[i][c];
+    }
+    __syncthreads();
+    // ---- |response| and fold: bin b feeds chroma ((b + 1) mod 36) / 3  (cq_to_chroma: 3 bins per semitone, rolled −1)
+    for (int i = tid; i < kChroma * kCqtTF; i += kCqtThreads) {
+        const int ch = i / kCqtTF, t = i % kCqtTF;
+        float s = 0.0f;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const int b = (3 * ch - 1 + q + kCqtBins) % kCqtBins;
+            const float re = sm.c[b][t], im = sm.c[kCqtBins + b][t];
+            s += sqrtf(re * re + im * im);
+        }
+        sm.chroma[ch][t] += s;
+    }
+    // the next octave's first __syncthreads orders these reads before sm.c / sm.sig are rewritten
+}
+
+struct PyrOffsets {
+    size_t off[kOctaves + 1];  // float offset of level o (1..6) inside a segment's pyramid; off[7] = stride
+};
+
+__global__ void __launch_bounds__(kCqtThreads) cqt_chroma_kernel(const float *__restrict__ audio,
+                                                                 const int64_t *__restrict__ seg_off,
+                                                                 const int32_t *__restrict__ seg_len,
+                                                                 const float *__restrict__ pyr, PyrOffsets po,
+                                                                 const int32_t *__restrict__ tuning_idx,
+                                                                 const float *__restrict__ Kall, int tile_stride,
+                                                                 double *__restrict__ partial) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CqtSmem &sm = *reinterpret_cast<CqtSmem *>(smem_raw);
+    const int seg = blockIdx.y;
+    const int n = seg_len[seg];
+    const int n_frames = cqt_frames(n);
+    const int t0 = blockIdx.x * kCqtTF;
+    if (t0 >= n_frames) return;
+    const int tid = threadIdx.x;
+    int tj = tuning_idx[seg];
+    tj = tj < 0 ? 0 : (tj >= kNTunings ? kNTunings - 1 : tj);
+    const float *Kj = Kall + (size_t)tj * kCqtNfft * kCqtRows;
+    for (int i = tid; i < kChroma * kCqtTF; i += kCqtThreads) (&sm.chroma[0][0])[i] = 0.0f;
+    const float *pseg = pyr + (size_t)seg * po.off[kOctaves];
+    cqt_octave<9>(sm, audio + seg_off[seg], n, t0, Kj, tid);
+    cqt_octave<8>(sm, pseg + po.off[1], level_len(n, 1), t0, Kj, tid);
+    cqt_octave<7>(sm, pseg + po.off[2], level_len(n, 2), t0, Kj, tid);
+    cqt_octave<6>(sm, pseg + po.off[3], level_len(n, 3), t0, Kj, tid);
+    cqt_octave<5>(sm, pseg + po.off[4], level_len(n, 4), t0, Kj, tid);
+    cqt_octave<4>(sm, pseg + po.off[5], level_len(n, 5), t0, Kj, tid);
+    cqt_octave<3>(sm, pseg + po.off[6], level_len(n, 6), t0, Kj, tid);
+    __syncthreads();
+    // ---- librosa.util.normalize(norm=inf) per frame, then the tile's sum over frames (float64)
+    if (tid < 32) {
+        const int t = tid;
+        const bool valid = (t0 + t) < n_frames;
+        float mx = 0.0f;
+#pragma unroll
+        for (int ch = 0; ch < kChroma; ++ch) mx = fmaxf(mx, sm.chroma[ch][t]);
+        const double len = (mx < 1.17549435e-38f) ? 1.0 : (double)mx;
+#pragma unroll
+        for (int ch = 0; ch < kChroma; ++ch) {
+            double v = valid ? (double)sm.chroma[ch][t] / len : 0.0;
+            v = warp_sum(v);
+            if (t == 0) partial[((size_t)seg * tile_stride + blockIdx.x) * kChroma + ch] = v;
+        }
+    }
+}
+
+// mean over frames: one warp per segment sums the tile partials in tile order
+__global__ void __launch_bounds__(32) chroma_mean_kernel(const int32_t *__restrict__ seg_len, int tile_stride,
+                                                         const double *__restrict__ partial,
+                                                         double *__restrict__ chroma) {
+    const int seg = blockIdx.x;
+    const int n_frames = cqt_frames(seg_len[seg]);
+    const int n_tiles = (n_frames + kCqtTF - 1) / kCqtTF;
+    const int ch = threadIdx.x;
+    if (ch >= kChroma) return;
+    double s = 0.0;
+    for (int t = 0; t < n_tiles; ++t) s += partial[((size_t)seg * tile_stride + t) * kChroma + ch];
+    chroma[(size_t)seg * kChroma + ch] = s / (double)n_frames;
+}
+
+// pitch._cyclic_xcorr_peak: xcorr[k] = dot(src, roll(nc, -k)); first maximum; wrap lags > n/2
+__global__ void __launch_bounds__(64) cyclic_xcorr_kernel(const double *__restrict__ src, const double *__restrict__ nc,
+                                                          int n_pairs, int n_bins, int32_t *__restrict__ lag) {
+    const int p = blockIdx.x * 64 + threadIdx.x;
+    if (p >= n_pairs) return;
+    const double *a = src + (size_t)p * n_bins, *b = nc + (size_t)p * n_bins;
+    double best = -INFINITY;
+    int bk = 0;
+    for (int k = 0; k < n_bins; ++k) {
+        double s = 0.0;
+        for (int i = 0; i < n_bins; ++i) {
+            int j = i + k;
+            if (j >= n_bins) j -= n_bins;  // roll(nc, -k)[i] = nc[(i + k) mod n]
+            s = fma(a[i], b[j], s);
+        }
+        if (s > best) {
+            best = s;
+            bk = k;
+        }
+    }
+    if (bk > n_bins / 2) bk -= n_bins;
+    lag[p] = bk;
+}
+
+}  // namespace ncfa
+
+using namespace ncfa;
+
+static size_t tuning_frames(int max_seg_len) { return 1 + (size_t)max_seg_len / 512; }
+
+extern "C" size_t ncfa_tuning_workspace_bytes(int n_seg, int max_seg_len) {
+    if (n_seg <= 0 || max_seg_len < 0) return 0;
+    const size_t slots = (size_t)n_seg * tuning_frames(max_seg_len) * kPeakStride;
+    return align_up(slots * 4, 256) + align_up(slots, 256) + align_up((size_t)n_seg * tuning_frames(max_seg_len) * 4, 256);
+}
+
+extern "C" int ncfa_tuning_estimate_batched(const float *d_audio, const int64_t *d_seg_off, const int32_t *d_seg_len,
+                                            int n_seg, int max_seg_len, int sr, int32_t *d_tuning_idx,
+                                            void *d_workspace, size_t workspace_bytes, void *stream) {
+    NCFA_REQUIRE(n_seg >= 0 && n_seg <= 65535, "n_seg must be in [0, 65535] per call");
+    if (n_seg == 0) return NCFA_OK;
+    NCFA_REQUIRE(d_audio && d_seg_off && d_seg_len && d_tuning_idx && d_workspace, "null pointer");
+    NCFA_REQUIRE(max_seg_len >= 0 && sr > 0, "max_seg_len/sr");
+    if (workspace_bytes < ncfa_tuning_workspace_bytes(n_seg, max_seg_len)) {
+        set_error("tuning workspace too small");
+        return NCFA_E_WORKSPACE;
+    }
+    Tables tb;
+    int rc = get_tables(sr, &tb);
+    if (rc) return rc;
+    // piptrack frequency mask: fmin=150 <= fft_freq < min(4000, sr/2), fft_freq[k] = k · (1 / (n_fft · (1/sr)))
+    const double val = 1.0 / (2048.0 * (1.0 / (double)sr));
+    const double fmax = fmin(4000.0, (double)sr / 2.0);
+    int kmin = 1, kmax = 1023;
+    while (kmin < 1024 && !((double)kmin * val >= 150.0)) ++kmin;
+    while (kmax > 0 && !((double)kmax * val < fmax)) --kmax;
+    NCFA_REQUIRE(kmin <= kmax && (kmax - kmin + 2) / 2 <= kPeakStride, "piptrack band does not fit the peak buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t frames = tuning_frames(max_seg_len);
+    const size_t slots = (size_t)n_seg * frames * kPeakStride;
+    char *wp = (char *)d_workspace;
+    float *pk_mag = (float *)wp;
+    wp += align_up(slots * 4, 256);
+    uint8_t *pk_bin = (uint8_t *)wp;
+    wp += align_up(slots, 256);
+    int32_t *pk_cnt = (int32_t *)wp;
+    static bool attr_done = false;
+    if (!attr_done) {
+        NCFA_CUDA_OK(cudaFuncSetAttribute(tuning_peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(TuningSmem)));
+        attr_done = true;
+    }
+    {
+        ProfScope _p("tuning_peaks_kernel", st);
+        dim3 g((unsigned)((frames + kTunFramesPerTile - 1) / kTunFramesPerTile), n_seg);
+        tuning_peaks_kernel<<<g, kTunThreads, sizeof(TuningSmem), st>>>(d_audio, d_seg_off, d_seg_len, (int)frames, kmin,
+                                                                         kmax, (double)sr / 2048.0, tb, pk_mag, pk_bin,
+                                                                         pk_cnt);
+    }
+    NCFA_LAUNCH_OK("tuning_peaks_kernel");
+    {
+        ProfScope _p("tuning_pick_kernel", st);
+        tuning_pick_kernel<<<n_seg, 256, 0, st>>>(d_seg_len, (int)frames, pk_mag, pk_bin, pk_cnt, d_tuning_idx);
+    }
+    NCFA_LAUNCH_OK("tuning_pick_kernel");
+    return NCFA_OK;
+}
+
+static int chroma_tiles(int max_seg_len) { return (cqt_frames(max_seg_len) + kCqtTF - 1) / kCqtTF; }
+
+extern "C" size_t ncfa_chroma_workspace_bytes(int n_seg, int max_seg_len) {
+    if (n_seg <= 0 || max_seg_len < 0) return 0;
+    size_t off[kOctaves + 1];
+    pyramid_layout(max_seg_len, off);
+    return align_up((size_t)n_seg * off[kOctaves] * 4 + 16, 256) +
+           align_up((size_t)n_seg * chroma_tiles(max_seg_len) * kChroma * 8, 256);
+}
+
+extern "C" int ncfa_chroma_mean_batched(const float *d_audio, const int64_t *d_seg_off, const int32_t *d_seg_len,
+                                        int n_seg, int max_seg_len, int sr, const int32_t *d_tuning_idx,
+                                        double *d_chroma, void *d_workspace, size_t workspace_bytes, void *stream) {
+    NCFA_REQUIRE(n_seg >= 0 && n_seg <= 65535, "n_seg must be in [0, 65535] per call");
+    if (n_seg == 0) return NCFA_OK;
+    NCFA_REQUIRE(d_audio && d_seg_off && d_seg_len && d_tuning_idx && d_chroma && d_workspace, "null pointer");
+    NCFA_REQUIRE(max_seg_len >= 0, "max_seg_len");
+    NCFA_REQUIRE(sr == 22050, "the CQT path is laid out for sr = 22050 (7 octaves from C1, n_fft 1024, no early downsampling)");
+    if (workspace_bytes < ncfa_chroma_workspace_bytes(n_seg, max_seg_len)) {
+        set_error("chroma workspace too small");
+        return NCFA_E_WORKSPACE;
+    }
+    ChromaTables ct;
+    int rc = get_chroma_tables(sr, &ct);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    PyrOffsets po;
+    pyramid_layout(max_seg_len, po.off);
+    const size_t stride = po.off[kOctaves];
+    float *pyr = (float *)d_workspace;
+    double *partial = (double *)((char *)d_workspace + align_up((size_t)n_seg * stride * 4 + 16, 256));
+    for (int level = 1; level < kOctaves; ++level) {
+        const int n_out = level_len(max_seg_len, level);
+        if (n_out <= 0) continue;
+        ProfScope _p("decimate2_kernel", st);
+        dim3 g((n_out + 255) / 256, n_seg);
+        decimate2_kernel<<<g, 256, 0, st>>>(d_audio, d_seg_off, d_seg_len, level, pyr, stride,
+                                            level >= 2 ? po.off[level - 1] : 0, po.off[level], ct.hb);
+        NCFA_LAUNCH_OK("decimate2_kernel");
+    }
+    static bool attr_done = false;
+    if (!attr_done) {
+        NCFA_CUDA_OK(cudaFuncSetAttribute(cqt_chroma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(CqtSmem)));
+        attr_done = true;
+    }
+    const int tiles = chroma_tiles(max_seg_len);
+    {
+        ProfScope _p("cqt_chroma_kernel", st);
+        dim3 g(tiles, n_seg);
+        cqt_chroma_kernel<<<g, kCqtThreads, sizeof(CqtSmem), st>>>(d_audio, d_seg_off, d_seg_len, pyr, po, d_tuning_idx,
+                                                                    ct.K, tiles, partial);
+    }
+    NCFA_LAUNCH_OK("cqt_chroma_kernel");
+    {
+        ProfScope _p("chroma_mean_kernel", st);
+        chroma_mean_kernel<<<n_seg, 32, 0, st>>>(d_seg_len, tiles, partial, d_chroma);
+    }
+    NCFA_LAUNCH_OK("chroma_mean_kernel");
+    return NCFA_OK;
+}
+
+extern "C" int ncfa_cyclic_xcorr_batched(const double *d_src, const double *d_nc, int n_pairs, int n_bins,
+                                         int32_t *d_lag, void *stream) {
+    NCFA_REQUIRE(n_pairs >= 0 && n_bins > 0, "n_pairs/n_bins");
+    if (n_pairs == 0) return NCFA_OK;
+    NCFA_REQUIRE(d_src && d_nc && d_lag, "null pointer");
+    {
+        ProfScope _p("cyclic_xcorr_kernel", (cudaStream_t)stream);
+        cyclic_xcorr_kernel<<<(n_pairs + 63) / 64, 64, 0, (cudaStream_t)stream>>>(d_src, d_nc, n_pairs, n_bins, d_lag);
+    }
+    NCFA_LAUNCH_OK("cyclic_xcorr_kernel");
+    return NCFA_OK;
+}
+
+// Host-side table builders, exported so that the CPU test-suite can check them without a GPU.
+extern "C" int ncfa_host_cqt_matrix(int sr, int tuning_index, float *h_K /* [1024][72] */) {
+    NCFA_REQUIRE(h_K && tuning_index >= 0 && tuning_index < kNTunings, "h_K/tuning_index");
+    std::vector<float> K;
+    int rc = build_cqt_matrix(sr, (double)tuning_index * 0.01 + (-0.5), K);
+    if (rc) return rc;
+    memcpy(h_K, K.data(), K.size() * sizeof(float));
+    return NCFA_OK;
+}
+
+extern "C" int ncfa_host_halfband_taps(double *h_taps /* [127] */) {
+    NCFA_REQUIRE(h_taps, "h_taps");
+    std::vector<double> h;
+    build_halfband(h);
+    memcpy(h_taps, h.data(), h.size() * sizeof(double));
+    return NCFA_OK;
+}

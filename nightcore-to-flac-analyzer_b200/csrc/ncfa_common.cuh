@@ -66,6 +66,8 @@ struct Tables {
     int sr;
 };
 int get_tables(int sr, Tables *out);
+// 127-tap half-band FIR (float64) on the current device (chroma.cu)
+int get_halfband_device(const double **out);
 
 // order-preserving float <-> uint encoding for atomicMax on floats
 __device__ __forceinline__ unsigned float_to_ordered(float f) {

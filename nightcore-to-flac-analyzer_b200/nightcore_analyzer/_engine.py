@@ -20,6 +20,8 @@ from ._native import check, lib
 # and the flux kernel (DESIGN.md "onset front-end").
 ONSET_WS_TARGET_BYTES = 96 << 20
 MAX_SEGS_PER_CALL = 65535
+# tuning peak lists / decimation pyramids of one launch (HBM scratch, reused across sub-batches)
+CHROMA_WS_TARGET_BYTES = 4 << 30
 
 
 def _ptr(t: Optional[torch.Tensor]) -> int:
@@ -263,6 +265,121 @@ class Engine:
                                             want_boot, want_idx)
         return (out.cpu().numpy(), None if boot is None else boot.cpu().numpy(),
                 None if idx is None else idx.cpu().numpy())
+
+    # ------------------------------------------------------------------ pitch.py: tuning, CQT chroma, cyclic xcorr
+    def chroma_mean_dev(self, audio: torch.Tensor, seg_off: np.ndarray, seg_len: np.ndarray, sr: int,
+                        tuning_idx: Optional[torch.Tensor] = None):
+        """pitch._mean_chroma for every segment → (chroma float64 [n_seg, 12], tuning_idx int32 [n_seg]) on the
+        device.  ``tuning_idx`` given: skip librosa.estimate_tuning and use those histogram bins."""
+        n_seg = len(seg_len)
+        chroma = torch.empty((max(n_seg, 1), 12), dtype=torch.float64, device=self.device)
+        tun = torch.empty(max(n_seg, 1), dtype=torch.int32, device=self.device)
+        if n_seg == 0:
+            return chroma[:0], tun[:0]
+        if tuning_idx is not None:
+            tun[:n_seg] = tuning_idx.to(self.device, torch.int32)
+        d_off = self.to_dev(seg_off.astype(np.int64))
+        d_len = self.to_dev(seg_len.astype(np.int32))
+        mx_all = int(seg_len.max())
+        per_seg = max(lib.ncfa_tuning_workspace_bytes(1, mx_all), lib.ncfa_chroma_workspace_bytes(1, mx_all), 1)
+        per_call = max(1, min(MAX_SEGS_PER_CALL, CHROMA_WS_TARGET_BYTES // per_seg))
+        with torch.cuda.device(self.device):
+            st = self._stream()
+            for s in range(0, n_seg, per_call):
+                e = min(n_seg, s + per_call)
+                mx = int(seg_len[s:e].max())
+                if tuning_idx is None:
+                    need = lib.ncfa_tuning_workspace_bytes(e - s, mx)
+                    ws = self.workspace("chroma", need)
+                    check(lib.ncfa_tuning_estimate_batched(_ptr(audio), d_off.data_ptr() + 8 * s, d_len.data_ptr() + 4 * s,
+                                                           e - s, mx, sr, tun.data_ptr() + 4 * s, _ptr(ws), ws.numel(), st),
+                          "ncfa_tuning_estimate_batched")
+                    self.launches += 2
+                need = lib.ncfa_chroma_workspace_bytes(e - s, mx)
+                ws = self.workspace("chroma", need)
+                check(lib.ncfa_chroma_mean_batched(_ptr(audio), d_off.data_ptr() + 8 * s, d_len.data_ptr() + 4 * s, e - s,
+                                                   mx, sr, tun.data_ptr() + 4 * s, chroma.data_ptr() + 96 * s, _ptr(ws),
+                                                   ws.numel(), st),
+                      "ncfa_chroma_mean_batched")
+                self.launches += 8
+        return chroma[:n_seg], tun[:n_seg]
+
+    def cyclic_xcorr_dev(self, src: torch.Tensor, nc: torch.Tensor) -> torch.Tensor:
+        """pitch._cyclic_xcorr_peak for n pairs of float64 vectors [n, n_bins] → int32 lags."""
+        n, bins = src.shape
+        lag = torch.empty(max(n, 1), dtype=torch.int32, device=self.device)
+        if n == 0:
+            return lag[:0]
+        src, nc = src.contiguous(), nc.contiguous()
+        with torch.cuda.device(self.device):
+            check(lib.ncfa_cyclic_xcorr_batched(_ptr(src), _ptr(nc), n, bins, _ptr(lag), self._stream()),
+                  "ncfa_cyclic_xcorr_batched")
+        self.launches += 1
+        return lag[:n]
+
+    # ------------------------------------------------------------------ xcorr.py: candidate search
+    def xcorr_search_dev(self, a: torch.Tensor, b: torch.Tensor, a_pos: np.ndarray, b_lo: np.ndarray,
+                         n_cand: np.ndarray, win: int, stride: int, rms_gate: float):
+        """Strided normalised-dot-product search (xcorr.py:113-148) → (best_j int32, best_c float64) on the device."""
+        n_w = len(a_pos)
+        best_j = torch.empty(max(n_w, 1), dtype=torch.int32, device=self.device)
+        best_c = torch.empty(max(n_w, 1), dtype=torch.float64, device=self.device)
+        if n_w == 0:
+            return best_j[:0], best_c[:0]
+        max_cand = max(1, int(n_cand.max()))
+        d_pos, d_lo, d_nc = self.to_dev(a_pos.astype(np.int64)), self.to_dev(b_lo.astype(np.int64)), self.to_dev(
+            n_cand.astype(np.int32))
+        with torch.cuda.device(self.device):
+            need = lib.ncfa_xcorr_workspace_bytes(n_w, max_cand)
+            ws = self.workspace("xcorr", need)
+            check(lib.ncfa_xcorr_search_batched(_ptr(a), _ptr(b), _ptr(d_pos), _ptr(d_lo), _ptr(d_nc), n_w, max_cand,
+                                                int(win), int(stride), float(rms_gate), _ptr(best_j), _ptr(best_c),
+                                                _ptr(ws), ws.numel(), self._stream()),
+                  "ncfa_xcorr_search_batched")
+        self.launches += 2
+        return best_j[:n_w], best_c[:n_w]
+
+    # ------------------------------------------------------------------ xcorr.py: intro alignment
+    def align_envelope(self, audio: np.ndarray, sr: int, target_sr: int, hop: int) -> torch.Tensor:
+        """librosa.resample(sr → target_sr) then feature.rms(hop)[0].astype(float64), on the device.
+        Only power-of-two decimations are supported (the reference calls it with 22050 → 11025)."""
+        ratio = sr // target_sr if target_sr > 0 else 0
+        if target_sr * ratio != sr or ratio < 1 or (ratio & (ratio - 1)) != 0:
+            raise ValueError(f"align_envelope supports sr = target_sr·2^k only (got {sr} → {target_sr})")
+        cur = self.to_dev(audio if len(audio) else np.zeros(1, np.float32))
+        n = len(audio)
+        with torch.cuda.device(self.device):
+            st = self._stream()
+            while ratio > 1:
+                n_out = (n + 1) // 2
+                nxt = torch.empty(max(n_out, 1), dtype=torch.float32, device=self.device)
+                check(lib.ncfa_decimate2(_ptr(cur), n, _ptr(nxt), st), "ncfa_decimate2")
+                self.launches += 1
+                cur, n, ratio = nxt, n_out, ratio // 2
+            rms = self.rms_frames_dev(cur, n, 2048, hop)
+            out = torch.empty(rms.numel(), dtype=torch.float64, device=self.device)
+            check(lib.ncfa_f32_to_f64(_ptr(rms), rms.numel(), _ptr(out), st), "ncfa_f32_to_f64")
+            self.launches += 1
+        return out
+
+    def align_search(self, src_env: torch.Tensor, nc_env: torch.Tensor, n_str: np.ndarray, n_lag: np.ndarray):
+        """30-speed envelope correlation of xcorr.find_content_offset → (peak_idx int32, score float64) on the host."""
+        n_sp = len(n_str)
+        live = n_lag > 0
+        max_str = int(n_str[live].max())
+        max_lag = int(n_lag[live].max())
+        pk = torch.empty(n_sp, dtype=torch.int32, device=self.device)
+        sc = torch.empty(n_sp, dtype=torch.float64, device=self.device)
+        d_ns, d_nl = self.to_dev(n_str.astype(np.int32)), self.to_dev(n_lag.astype(np.int32))
+        with torch.cuda.device(self.device):
+            need = lib.ncfa_align_workspace_bytes(n_sp, max_str, max_lag)
+            ws = self.workspace("align", need)
+            check(lib.ncfa_align_search(_ptr(src_env), int(src_env.numel()), _ptr(nc_env), int(nc_env.numel()), _ptr(d_ns),
+                                        _ptr(d_nl), n_sp, max_str, max_lag, _ptr(pk), _ptr(sc), _ptr(ws), ws.numel(),
+                                        self._stream()),
+                  "ncfa_align_search")
+        self.launches += 3
+        return self.to_host(pk), self.to_host(sc)
 
     # ------------------------------------------------------------------ host conveniences
     def onset_strength(self, arrays: Sequence[np.ndarray], hop: int, sr: int) -> List[np.ndarray]:

@@ -50,12 +50,20 @@ _SIGNATURES = {
         [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, ctypes.POINTER(c_uint64), c_double, c_double, _P, _P,
          _P, _P, c_size_t, _P],
     ),
-    "ncfa_xcorr_search_batched": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "ncfa_tuning_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "ncfa_tuning_estimate_batched": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
     "ncfa_chroma_workspace_bytes": (c_size_t, [c_int, c_int]),
     "ncfa_chroma_mean_batched": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P]),
-    "ncfa_tuning_workspace_bytes": (c_size_t, [c_int, c_int]),
-    "ncfa_tuning_hist_batched": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
     "ncfa_cyclic_xcorr_batched": (c_int, [_P, _P, c_int, c_int, _P, _P]),
+    "ncfa_xcorr_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "ncfa_xcorr_search_batched": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_double, _P, _P, _P,
+                                          c_size_t, _P]),
+    "ncfa_decimate2": (c_int, [_P, c_int64, _P, _P]),
+    "ncfa_f32_to_f64": (c_int, [_P, c_int64, _P, _P]),
+    "ncfa_align_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "ncfa_align_search": (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P]),
+    "ncfa_host_cqt_matrix": (c_int, [c_int, c_int, _P]),
+    "ncfa_host_halfband_taps": (c_int, [_P]),
 }
 
 

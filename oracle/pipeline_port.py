@@ -209,3 +209,86 @@ def run_arrays(nc_audio: np.ndarray, src_audio: np.ndarray, sr: int = SAMPLE_RAT
     if return_window_count:
         return out, len(src_w) + len(nc_w)
     return out
+
+
+# ---------------------------------------------------------------------------------------------- xcorr.py
+XCORR_RMS_GATE = 1e-3     # xcorr.py:38
+ALIGN_SR = 11025          # xcorr.py:45
+ALIGN_HOP = 512
+
+
+def speed_xcorr_arrays(ya: np.ndarray, yb: np.ndarray, sr: int = 22050, n_windows: int = 20, window_sec: float = 3.0,
+                       search_range: float = 0.05, skip_edges: float = 0.10, return_indices: bool = False):
+    """xcorr.py:95-162 from the point where both files are loaded at `sr`: edge trim, 20 reference
+    windows of A, strided float32 cosine search in B (stride = win//4, first strict maximum), polyfit
+    slope + median quality.  Returns (slope, quality) [+ (a_pos, best_pb or -1 per window)]."""
+    min_len = min(len(ya), len(yb))
+    s, e = int(min_len * skip_edges), int(min_len * (1.0 - skip_edges))
+    ya, yb = ya[s:e], yb[s:e]
+    win = int(window_sec * sr)
+    search = int(search_range * len(yb))
+    stride = max(1, win // 4)
+    if len(ya) < win or len(yb) < win:
+        return ((1.0, 0.0), (np.zeros(0, np.int64), np.zeros(0, np.int64))) if return_indices else (1.0, 0.0)
+    a_positions = np.linspace(0, len(ya) - win, n_windows).astype(int)
+    picks = np.full(len(a_positions), -1, dtype=np.int64)
+    quals = np.zeros(len(a_positions))
+    for i, pa in enumerate(a_positions):
+        wa = ya[pa : pa + win]
+        if float(np.sqrt(np.mean(wa ** 2))) < XCORR_RMS_GATE:
+            continue
+        expected = int(pa * len(yb) / len(ya))
+        lo_b, hi_b = max(0, expected - search), min(len(yb) - win, expected + search)
+        if lo_b >= hi_b:
+            continue
+        norm_a = float(np.linalg.norm(wa))
+        if norm_a < 1e-10:
+            continue
+        best_c, best_pb = -1.0, expected
+        for pb in range(lo_b, hi_b, stride):
+            wb = yb[pb : pb + win]
+            norm_b = float(np.linalg.norm(wb))
+            if norm_b < 1e-10:
+                continue
+            c = float(np.dot(wa, wb) / (norm_a * norm_b))
+            if c > best_c:
+                best_c, best_pb = c, pb
+        if best_c > 0:
+            picks[i], quals[i] = best_pb, best_c
+    keep = picks >= 0
+    if keep.sum() < 3:
+        res = (1.0, 0.0)
+    else:
+        res = (float(np.polyfit(a_positions[keep].astype(float), picks[keep].astype(float), 1)[0]),
+               float(np.median(quals[keep])))
+    return (res, (a_positions.astype(np.int64), picks)) if return_indices else res
+
+
+def content_offset(src_audio: np.ndarray, nc_audio: np.ndarray, sr: int, speed_lo: float = 1.03, speed_hi: float = 1.50,
+                   n_speeds: int = 30, max_offset_sec: float = 120.0, return_debug: bool = False):
+    """xcorr.py:165-259: RMS envelopes at 11 025 Hz (hop 512), 30 candidate speeds, np.interp stretch,
+    np.correlate('valid') over the first max_offset frames, cosine-normalised peak."""
+    src_env = lr.rms(lr.resample(src_audio, sr, ALIGN_SR), 2048, ALIGN_HOP).astype(np.float64)
+    nc_env = lr.rms(lr.resample(nc_audio, sr, ALIGN_SR), 2048, ALIGN_HOP).astype(np.float64)
+    hop_sec = ALIGN_HOP / ALIGN_SR
+    max_frames = int(max_offset_sec / hop_sec)
+    best = (-1.0, 0.0, (speed_lo + speed_hi) / 2.0)
+    dbg = []
+    for speed in np.linspace(speed_lo, speed_hi, n_speeds):
+        n_st = int(len(nc_env) / speed)
+        if n_st < 4 or n_st >= len(src_env):
+            dbg.append(None)
+            continue
+        stretched = np.interp(np.linspace(0.0, 1.0, n_st), np.linspace(0.0, 1.0, len(nc_env)), nc_env)
+        search_len = min(max_frames, len(src_env) - n_st)
+        if search_len <= 0:
+            dbg.append(None)
+            continue
+        corr = np.correlate(src_env[: search_len + n_st], stretched, mode="valid")[: search_len + 1]
+        pk = int(np.argmax(corr))
+        denom = np.sqrt(float(np.sum(src_env[pk : pk + n_st] ** 2)) * float(np.sum(stretched ** 2)))
+        score = float(corr[pk]) / denom if denom > 1e-12 else 0.0
+        dbg.append((pk, score))
+        if score > best[0]:
+            best = (score, pk * hop_sec, speed)
+    return ((best[1], best[2]), dbg) if return_debug else (best[1], best[2])
