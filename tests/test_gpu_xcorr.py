@@ -42,7 +42,8 @@ def test_speed_xcorr_44k_and_batch(engine):
     assert res[1][1].tolist() == want[1][1].tolist() and res[0][0] == want[0][0]
     both = nx.estimate_speed_xcorr_batch([(c, d), (c, c)], SR)
     assert both[0] == nx.estimate_speed_xcorr_arrays(c, d, SR)
-    assert both[1][0] == port.speed_xcorr_arrays(c, c, SR)[0] and abs(both[1][1] - 1.0) < 1e-5
+    w_same = port.speed_xcorr_arrays(c, c, SR)     # identical files: the strided grid need not contain the true offset
+    assert both[1][0] == w_same[0] and abs(both[1][1] - w_same[1]) <= 1e-5
 
 
 def test_speed_xcorr_sentinels(engine):
