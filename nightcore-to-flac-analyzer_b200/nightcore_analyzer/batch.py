@@ -43,10 +43,22 @@ class StagedBatch:
         return len(self.off) // 2
 
 
-def stage_pairs(pairs: Sequence[Tuple[np.ndarray, np.ndarray]], sr: int = SAMPLE_RATE,
-                pinned: Optional[torch.Tensor] = None) -> StagedBatch:
-    """Copy [(nc_audio, src_audio), ...] into one device buffer (through pinned host memory)."""
-    eng = _engine.get_engine()
+@dataclass
+class PinnedBatch:
+    """Tracks of a batch laid out in pinned host memory, ready for one H2D copy."""
+    pinned: torch.Tensor         # float32, pinned
+    off: np.ndarray              # int64 [2P]
+    length: np.ndarray           # int64 [2P]
+    sr: int
+
+    @property
+    def n_pairs(self) -> int:
+        return len(self.off) // 2
+
+
+def pin_pairs(pairs: Sequence[Tuple[np.ndarray, np.ndarray]], sr: int = SAMPLE_RATE,
+              pinned: Optional[torch.Tensor] = None) -> PinnedBatch:
+    """Lay [(nc_audio, src_audio), ...] out in one pinned host buffer (4-sample aligned track starts)."""
     tracks = [np.asarray(t, dtype=np.float32) for p in pairs for t in p]
     length = np.array([len(t) for t in tracks], dtype=np.int64)
     padded = (length + 3) // 4 * 4
@@ -59,8 +71,24 @@ def stage_pairs(pairs: Sequence[Tuple[np.ndarray, np.ndarray]], sr: int = SAMPLE
     hn = pinned.numpy()
     for t, o in zip(tracks, off):
         hn[o : o + len(t)] = t
-    audio = pinned[: max(total, 4)].to(eng.device, non_blocking=True)
-    return StagedBatch(audio=audio, off=off, length=length, sr=sr, h2d_bytes=4 * total)
+    return PinnedBatch(pinned=pinned, off=off, length=length, sr=sr)
+
+
+def upload(pb: PinnedBatch, n_pairs: Optional[int] = None) -> StagedBatch:
+    """One asynchronous H2D copy of the first ``n_pairs`` pairs of a pinned batch."""
+    eng = _engine.get_engine()
+    k = pb.n_pairs if n_pairs is None else min(int(n_pairs), pb.n_pairs)
+    off, length = pb.off[: 2 * k], pb.length[: 2 * k]
+    total = int(off[-1] + (length[-1] + 3) // 4 * 4) if k else 0
+    audio = pb.pinned[: max(total, 4)].to(eng.device, non_blocking=True)
+    eng.h2d_bytes += 4 * total
+    return StagedBatch(audio=audio, off=off.copy(), length=length.copy(), sr=pb.sr, h2d_bytes=4 * total)
+
+
+def stage_pairs(pairs: Sequence[Tuple[np.ndarray, np.ndarray]], sr: int = SAMPLE_RATE,
+                pinned: Optional[torch.Tensor] = None) -> StagedBatch:
+    """Copy [(nc_audio, src_audio), ...] into one device buffer (through pinned host memory)."""
+    return upload(pin_pairs(pairs, sr, pinned))
 
 
 def _window_starts(n: int, win_n: int, hop_n: int) -> np.ndarray:
