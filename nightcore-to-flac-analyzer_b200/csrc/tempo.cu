@@ -10,6 +10,13 @@
 // and all three sums slide from t to t+1 with one remove, one add and one rotation (float64).
 // One thread owns one lag k and walks a chunk of frames; the per-frame normaliser R_t[0] is
 // computed first by direct summation (exact, no cancellation).
+//
+// Only the argmax lag is observable, and every inf-normalised tempogram value is <= 1, so
+// score_k = log1p(1e6·tg_k) + prior_k <= log1p(1e6) + prior_k.  The lags are therefore evaluated
+// branch-and-bound: phase 1 covers the lag blocks within half an octave of the prior's centre and
+// yields a best score s*; phase 2 evaluates only the remaining blocks that contain a lag with
+// prior_k > s* − log1p(1e6) − 1e-6 (the prior is unimodal, so that set is one interval).  Lags outside
+// cannot win, so the argmax is unchanged; typically ~80 % of the 2691 hop-64 lags are never touched.
 #include "ncfa_common.cuh"
 
 namespace ncfa {
@@ -67,12 +74,24 @@ __global__ void __launch_bounds__(kLagThreads) tg_lag_kernel(const float *__rest
                                                              int W, int chunk, int n_chunks, int k_min,
                                                              const double2 *__restrict__ trig,
                                                              const double *__restrict__ r0,
+                                                             const int2 *__restrict__ todo,
+                                                             const int2 *__restrict__ done,
                                                              double *__restrict__ partial) {
     extern __shared__ double xs[];  // chunk + W
     const int seg = blockIdx.z;
     const int n = env_len[seg];
     const int t0 = blockIdx.y * chunk;
     if (t0 >= n) return;
+    {
+        // lag block [kb, ke): evaluate iff it intersects todo[seg] and is not inside done[seg] (both block aligned)
+        const int kb = k_min + blockIdx.x * kLagThreads, ke = kb + kLagThreads;
+        const int2 td = todo[seg];
+        if (ke <= td.x || kb >= td.y) return;
+        if (done != nullptr) {
+            const int2 dn = done[seg];
+            if (kb >= dn.x && kb < dn.y) return;
+        }
+    }
     const int t1 = min(n, t0 + chunk);
     const float *on = onset + onset_off[seg];
     const int p = W / 2;
@@ -139,13 +158,96 @@ __global__ void __launch_bounds__(kLagThreads) tg_lag_kernel(const float *__rest
     if (active) partial[((size_t)seg * n_chunks + blockIdx.y) * W + k] = acc;
 }
 
+__device__ __forceinline__ double tg_score(const double *__restrict__ partial, int seg, int n_chunks, int used_chunks,
+                                           int W, int k, int n, int hop, int sr, double l2s) {
+    double s = 0.0;
+    for (int c = 0; c < used_chunks; ++c) s += partial[((size_t)seg * n_chunks + c) * W + k];
+    const double tg = s / (double)n;
+    const double bpm = (60.0 * (double)sr) / ((double)hop * (double)k);
+    const double d = log2(bpm) - l2s;
+    return log1p(1e6 * tg) + (-0.5 * (d * d));
+}
+
+__device__ __forceinline__ int2 block_align(int klo, int khi, int k_min, int W) {  // [klo, khi] → block-aligned [x, y)
+    const int b0 = (klo - k_min) / kLagThreads, b1 = (khi - k_min) / kLagThreads;
+    int y = k_min + (b1 + 1) * kLagThreads;
+    return make_int2(k_min + b0 * kLagThreads, y);
+}
+
+// phase-1 range: the lag blocks within ±half an octave of the prior centre (one thread per segment)
+__global__ void tg_range_kernel(int n_seg, int W, int k_min, int hop, int sr, const double *__restrict__ start_bpm,
+                                int2 *__restrict__ range1) {
+    const int seg = blockIdx.x * blockDim.x + threadIdx.x;
+    if (seg >= n_seg) return;
+    const double k0 = (60.0 * (double)sr) / ((double)hop * start_bpm[seg]);
+    int klo = (int)floor(k0 / 1.4142135623730951), khi = (int)ceil(k0 * 1.4142135623730951);
+    if (!(k0 == k0) || k0 <= 0.0) klo = khi = k_min;
+    klo = klo < k_min ? k_min : (klo > W - 1 ? W - 1 : klo);
+    khi = khi < klo ? klo : (khi > W - 1 ? W - 1 : khi);
+    range1[seg] = block_align(klo, khi, k_min, W);
+}
+
+// after phase 1: s* = best score so far; phase-2 range = hull of lags whose prior alone could still beat it
+__global__ void __launch_bounds__(256) tg_bound_kernel(const int32_t *__restrict__ env_len, int W, int n_chunks, int chunk,
+                                                       int k_min, int hop, int sr, const double *__restrict__ start_bpm,
+                                                       const double *__restrict__ partial, const int2 *__restrict__ range1,
+                                                       int2 *__restrict__ range2, int2 *__restrict__ hull) {
+    __shared__ double s_best[256];
+    __shared__ int s_lo[256], s_hi[256];
+    const int seg = blockIdx.x;
+    const int n = env_len[seg];
+    const int used_chunks = (n + chunk - 1) / chunk;
+    const double l2s = log2(start_bpm[seg]);
+    const int2 r1 = range1[seg];
+    double best = -INFINITY;
+    for (int k = r1.x + threadIdx.x; k < r1.y && k < W; k += 256)
+        best = fmax(best, tg_score(partial, seg, n_chunks, used_chunks, W, k, n, hop, sr, l2s));
+    s_best[threadIdx.x] = best;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s_best[threadIdx.x] = fmax(s_best[threadIdx.x], s_best[threadIdx.x + o]);
+        __syncthreads();
+    }
+    best = s_best[0];
+    // a NaN score (degenerate envelope) disables pruning: evaluate everything
+    const double cut = (best == best) ? best - 13.815511557963774 - 1e-6 : -INFINITY;  // log1p(1e6)
+    int lo = 0x7fffffff, hi = -1;
+    for (int k = k_min + threadIdx.x; k < W; k += 256) {
+        const double bpm = (60.0 * (double)sr) / ((double)hop * (double)k);
+        const double d = log2(bpm) - l2s;
+        if (!(-0.5 * (d * d) <= cut)) {
+            lo = k < lo ? k : lo;
+            hi = k > hi ? k : hi;
+        }
+    }
+    s_lo[threadIdx.x] = lo;
+    s_hi[threadIdx.x] = hi;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            s_lo[threadIdx.x] = min(s_lo[threadIdx.x], s_lo[threadIdx.x + o]);
+            s_hi[threadIdx.x] = max(s_hi[threadIdx.x], s_hi[threadIdx.x + o]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        int2 r2 = r1;
+        if (s_hi[0] >= 0) r2 = block_align(s_lo[0], s_hi[0], k_min, W);
+        range2[seg] = r2;
+        hull[seg] = make_int2(min(r1.x, r2.x), max(r1.y, r2.y));
+        // blocks between r1 and r2 (if disjoint) must be evaluated too so that the hull holds no garbage
+        range2[seg] = hull[seg];
+    }
+}
+
 // pass 3: tg[k] = Σ_chunks partial / n;  lag = argmax_k log1p(1e6·tg[k]) − ½(log2(bpm_k) − log2(start_bpm))²
 __global__ void __launch_bounds__(256) tg_argmax_kernel(const float *__restrict__ onset,
                                                         const int64_t *__restrict__ onset_off,
                                                         const int32_t *__restrict__ env_len, int W, int n_chunks,
                                                         int chunk, int k_min, int hop, int sr,
                                                         const double *__restrict__ start_bpm,
-                                                        const double *__restrict__ partial, int32_t *__restrict__ lag_out) {
+                                                        const double *__restrict__ partial,
+                                                        const int2 *__restrict__ hull, int32_t *__restrict__ lag_out) {
     __shared__ double s_best[256];
     __shared__ int s_idx[256];
     __shared__ int s_any;
@@ -166,13 +268,9 @@ __global__ void __launch_bounds__(256) tg_argmax_kernel(const float *__restrict_
     const double l2s = log2(start_bpm[seg]);
     double best = -INFINITY;
     int bidx = 0x7fffffff;
-    for (int k = k_min + threadIdx.x; k < W; k += 256) {
-        double s = 0.0;
-        for (int c = 0; c < used_chunks; ++c) s += partial[((size_t)seg * n_chunks + c) * W + k];
-        const double tg = s / (double)n;
-        const double bpm = (60.0 * (double)sr) / ((double)hop * (double)k);
-        const double d = log2(bpm) - l2s;
-        const double score = log1p(1e6 * tg) + (-0.5 * (d * d));
+    const int2 hl = hull[seg];
+    for (int k = hl.x + threadIdx.x; k < hl.y && k < W; k += 256) {
+        const double score = tg_score(partial, seg, n_chunks, used_chunks, W, k, n, hop, sr, l2s);
         if (score > best) {  // ascending k: strict > keeps the first maximum
             best = score;
             bidx = k;
@@ -206,7 +304,8 @@ extern "C" size_t ncfa_tempo_workspace_bytes(int n_seg, int max_env_len, int win
     const int chunk = tempo_chunk(max_env_len);
     const size_t n_chunks = (max_env_len + chunk - 1) / chunk;
     return align_up((size_t)win_length * sizeof(double2), 256) + align_up((size_t)win_length * 8, 256) +
-           align_up((size_t)n_seg * max_env_len * 8, 256) + align_up((size_t)n_seg * n_chunks * win_length * 8, 256);
+           align_up((size_t)n_seg * max_env_len * 8, 256) + align_up((size_t)n_seg * n_chunks * win_length * 8, 256) +
+           3 * align_up((size_t)n_seg * sizeof(int2), 256);
 }
 
 extern "C" int ncfa_tempo_lag_batched(const float *d_onset, const int64_t *d_onset_off, const int32_t *d_env_len,
@@ -233,6 +332,12 @@ extern "C" int ncfa_tempo_lag_batched(const float *d_onset, const int64_t *d_ons
     double *r0 = (double *)wp;
     wp += align_up((size_t)n_seg * max_env_len * 8, 256);
     double *partial = (double *)wp;
+    wp += align_up((size_t)n_seg * n_chunks * W * 8, 256);
+    int2 *range1 = (int2 *)wp;
+    wp += align_up((size_t)n_seg * sizeof(int2), 256);
+    int2 *range2 = (int2 *)wp;
+    wp += align_up((size_t)n_seg * sizeof(int2), 256);
+    int2 *hull = (int2 *)wp;
 
     // first lag whose bpm is below max_tempo = 320 (logprior[:max_idx] = -inf)
     int k_min = 1;
@@ -254,6 +359,11 @@ extern "C" int ncfa_tempo_lag_batched(const float *d_onset, const int64_t *d_ons
         NCFA_LAUNCH_OK("tg_r0_kernel");
     }
     {
+        ProfScope _p("tg_range_kernel", st);
+        tg_range_kernel<<<(n_seg + 127) / 128, 128, 0, st>>>(n_seg, W, k_min, hop, sr, d_start_bpm, range1);
+    }
+    NCFA_LAUNCH_OK("tg_range_kernel");
+    {
         size_t sh = (size_t)(chunk + W) * 8;
         static size_t sh_set = 0;
         if (sh > 48 * 1024 && sh > sh_set) {
@@ -264,14 +374,26 @@ extern "C" int ncfa_tempo_lag_batched(const float *d_onset, const int64_t *d_ons
         {
             ProfScope _p("tg_lag_kernel", st);
             tg_lag_kernel<<<g, kLagThreads, sh, st>>>(d_onset, d_onset_off, d_env_len, max_env_len, W, chunk, n_chunks,
-                                                  k_min, trig, r0, partial);
+                                                  k_min, trig, r0, range1, nullptr, partial);
+        }
+        NCFA_LAUNCH_OK("tg_lag_kernel");
+        {
+            ProfScope _p("tg_bound_kernel", st);
+            tg_bound_kernel<<<n_seg, 256, 0, st>>>(d_env_len, W, n_chunks, chunk, k_min, hop, sr, d_start_bpm, partial,
+                                               range1, range2, hull);
+        }
+        NCFA_LAUNCH_OK("tg_bound_kernel");
+        {
+            ProfScope _p("tg_lag_kernel", st);
+            tg_lag_kernel<<<g, kLagThreads, sh, st>>>(d_onset, d_onset_off, d_env_len, max_env_len, W, chunk, n_chunks,
+                                                  k_min, trig, r0, range2, range1, partial);
         }
         NCFA_LAUNCH_OK("tg_lag_kernel");
     }
     {
         ProfScope _p("tg_argmax_kernel", st);
         tg_argmax_kernel<<<n_seg, 256, 0, st>>>(d_onset, d_onset_off, d_env_len, W, n_chunks, chunk, k_min, hop, sr,
-                                            d_start_bpm, partial, d_lag);
+                                            d_start_bpm, partial, hull, d_lag);
     }
     NCFA_LAUNCH_OK("tg_argmax_kernel");
     return NCFA_OK;

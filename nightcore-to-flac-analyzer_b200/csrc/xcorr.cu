@@ -334,7 +334,7 @@ extern "C" int ncfa_align_search(const double *d_src_env, int n_src, const doubl
     if (n_speeds == 0) return NCFA_OK;
     NCFA_REQUIRE(d_src_env && d_nc_env && d_n_stretched && d_n_lags && d_peak_idx && d_score && d_workspace, "null pointer");
     NCFA_REQUIRE(n_src > 0 && n_nc > 1 && max_stretched >= 2 && max_lags > 0, "n_src/n_nc/max_stretched/max_lags");
-    NCFA_REQUIRE(max_stretched + max_lags - 1 <= n_src, "lags + stretched length exceed the source envelope");
+    // per speed n_stretched[s] + n_lags[s] − 1 <= n_src by construction (xcorr.py:232: search_len <= n_src − n_stretched)
     if (workspace_bytes < ncfa_align_workspace_bytes(n_speeds, max_stretched, max_lags)) {
         set_error("align workspace too small");
         return NCFA_E_WORKSPACE;

@@ -162,7 +162,7 @@ class Engine:
                         _ptr(onset), d_env_off.data_ptr() + 8 * s, d_env_len.data_ptr() + 4 * s, e - s, mx, hop, sr,
                         d_start_bpm.data_ptr() + 8 * s, lag.data_ptr() + 4 * s, _ptr(ws), ws.numel(), st),
                     "ncfa_tempo_lag_batched")
-                self.launches += 4
+                self.launches += 7
         return lag[:n_seg]
 
     # ------------------------------------------------------------------ beat tracker
