@@ -245,49 +245,40 @@ __host__ __device__ inline void pyramid_layout(int max_len, size_t off[kOctaves 
 }
 
 // ------------------------------------------------------------------------------------------------ tuning
-constexpr int kTunWarps = 4;
+constexpr int kTunWarps = 16;
 constexpr int kTunThreads = kTunWarps * 32;
-constexpr int kTunFramesPerTile = 8;
-constexpr int kTunTile = (kTunFramesPerTile - 1) * 512 + 2048;
 
 struct TuningSmem {
-    float tile[kTunTile];
     float hann[2048];
     float2 tw[1024];
     float2 scr[kTunWarps][32 * kScrStride];
 };
 
-__global__ void __launch_bounds__(kTunThreads) tuning_peaks_kernel(const float *__restrict__ audio,
-                                                                   const int64_t *__restrict__ seg_off,
-                                                                   const int32_t *__restrict__ seg_len, int frame_stride,
-                                                                   int kmin, int kmax, double hz_per_bin, Tables tb,
-                                                                   float *__restrict__ pk_mag,
-                                                                   uint8_t *__restrict__ pk_bin,
-                                                                   int32_t *__restrict__ pk_cnt) {
+// persistent CTAs (one per SM), one warp per frame, frames read straight from global memory (see stft_onset.cu)
+__global__ void __launch_bounds__(kTunThreads, 1) tuning_peaks_kernel(const float *__restrict__ audio,
+                                                                      const int64_t *__restrict__ seg_off,
+                                                                      const int32_t *__restrict__ seg_len, int n_seg,
+                                                                      int frame_stride, int kmin, int kmax,
+                                                                      double hz_per_bin, Tables tb,
+                                                                      float *__restrict__ pk_mag,
+                                                                      uint8_t *__restrict__ pk_bin,
+                                                                      int32_t *__restrict__ pk_cnt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TuningSmem &sm = *reinterpret_cast<TuningSmem *>(smem_raw);
-    const int seg = blockIdx.y;
-    const int len = seg_len[seg];
-    const int n_frames = 1 + len / 512;
-    const int f0 = blockIdx.x * kTunFramesPerTile;
-    if (f0 >= n_frames) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float *src = audio + seg_off[seg];
     for (int i = tid; i < 2048; i += kTunThreads) sm.hann[i] = tb.hann[i];
     for (int i = tid; i < 1024; i += kTunThreads) sm.tw[i] = tb.tw1024[i];
-    const int nf_tile = min(kTunFramesPerTile, n_frames - f0);
-    const int tile_n = (nf_tile - 1) * 512 + 2048;
-    const int64_t pos0 = (int64_t)f0 * 512 - 1024;
-    for (int i = tid; i < tile_n; i += kTunThreads) {
-        const int64_t p = pos0 + i;
-        sm.tile[i] = (p >= 0 && p < len) ? __ldg(src + p) : 0.0f;
-    }
     __syncthreads();
     const cf twl = cf{tb.tw2048[lane].x, tb.tw2048[lane].y};
     float2 *scr = sm.scr[warp];
     float *S = reinterpret_cast<float *>(scr);
-    for (int fl = warp; fl < nf_tile; fl += kTunWarps) {
-        warp_power_spectrum(sm.tile + fl * 512, sm.hann, sm.tw, scr, twl, lane);
+    const int64_t total = (int64_t)n_seg * frame_stride;
+    for (int64_t item = (int64_t)blockIdx.x * kTunWarps + warp; item < total; item += (int64_t)gridDim.x * kTunWarps) {
+        const int seg = (int)(item / frame_stride);
+        const int frame = (int)(item - (int64_t)seg * frame_stride);
+        const int len = seg_len[seg];
+        if (frame >= 1 + len / 512) continue;
+        warp_power_spectrum_global(audio + seg_off[seg], (int64_t)frame * 512 - 1024, len, sm.hann, sm.tw, scr, twl, lane);
         float mx = 0.0f;
         for (int k = lane; k < 1025; k += 32) {
             const float m = sqrtf(S[k]);
@@ -297,7 +288,7 @@ __global__ void __launch_bounds__(kTunThreads) tuning_peaks_kernel(const float *
         mx = warp_max(mx);
         __syncwarp();
         const float ref = 0.1f * mx;  // threshold · max over the frame
-        const size_t slot0 = ((size_t)seg * frame_stride + (f0 + fl)) * kPeakStride;
+        const size_t slot0 = ((size_t)seg * frame_stride + frame) * kPeakStride;
         int count = 0;
         for (int kb = kmin; kb <= kmax; kb += 32) {
             const int k = kb + lane;
@@ -332,7 +323,7 @@ __global__ void __launch_bounds__(kTunThreads) tuning_peaks_kernel(const float *
             }
             count += __popc(m);
         }
-        if (lane == 0) pk_cnt[(size_t)seg * frame_stride + f0 + fl] = count;
+        if (lane == 0) pk_cnt[(size_t)seg * frame_stride + frame] = count;
         __syncwarp();
     }
 }
@@ -441,9 +432,11 @@ __global__ void __launch_bounds__(256) decimate2_kernel(const float *__restrict_
     __syncthreads();
     const int i = i0 + threadIdx.x;
     if (i >= n_out) return;
-    double acc = 0.0;
+    // half-band: the taps at odd offsets from the centre are the only non-zero ones besides the centre itself
+    // (the others are sin(mπ)-rounding residue below 1e-17 and are skipped)
+    double acc = h[(kHbTaps - 1) / 2] * (double)xin[2 * threadIdx.x + (kHbTaps - 1) / 2];
 #pragma unroll 8
-    for (int k = 0; k < kHbTaps; ++k) acc = fma(h[k], (double)xin[2 * threadIdx.x + k], acc);
+    for (int k = 0; k < kHbTaps; k += 2) acc = fma(h[k], (double)xin[2 * threadIdx.x + k], acc);
     out[i] = (float)(acc * 1.4142135623730951);
 }
 
@@ -684,11 +677,18 @@ extern "C" int ncfa_tuning_estimate_batched(const float *d_audio, const int64_t 
         attr_done = true;
     }
     {
+        static int n_sm = 0;
+        if (n_sm == 0) {
+            int dev = 0;
+            NCFA_CUDA_OK(cudaGetDevice(&dev));
+            NCFA_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        }
+        const int64_t groups = ((int64_t)n_seg * (int64_t)frames + kTunWarps - 1) / kTunWarps;
+        const int grid = (int)(groups < n_sm ? groups : n_sm);
         ProfScope _p("tuning_peaks_kernel", st);
-        dim3 g((unsigned)((frames + kTunFramesPerTile - 1) / kTunFramesPerTile), n_seg);
-        tuning_peaks_kernel<<<g, kTunThreads, sizeof(TuningSmem), st>>>(d_audio, d_seg_off, d_seg_len, (int)frames, kmin,
-                                                                         kmax, (double)sr / 2048.0, tb, pk_mag, pk_bin,
-                                                                         pk_cnt);
+        tuning_peaks_kernel<<<grid, kTunThreads, sizeof(TuningSmem), st>>>(d_audio, d_seg_off, d_seg_len, n_seg, (int)frames,
+                                                                           kmin, kmax, (double)sr / 2048.0, tb, pk_mag,
+                                                                           pk_bin, pk_cnt);
     }
     NCFA_LAUNCH_OK("tuning_peaks_kernel");
     {

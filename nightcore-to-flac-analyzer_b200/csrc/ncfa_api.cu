@@ -1,6 +1,7 @@
 // Library plumbing: error string, version, constant tables (Hann, twiddles, Slaney mel bank).
 #include <math.h>
 #include <stdarg.h>
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <string>
@@ -135,6 +136,35 @@ int get_tables(int sr, Tables *out) {
     }
     DeviceTables dt;
     int rc;
+    // lane-transposed copy (see Tables)
+    {
+        int rows = 0;
+        for (int q = 0; q < 4; ++q) {
+            int mw = 0;
+            for (int l = 0; l < 32; ++l) {
+                const int m = mel_band_of(q, l);
+                mw = std::max(mw, start[m + 1] - start[m]);
+            }
+            dt.t.mel_qoff[q] = rows;
+            dt.t.mel_qw[q] = mw;
+            rows += mw;
+        }
+        dt.t.mel_wt_rows = rows;
+        if (rows > 128) {
+            set_error("transposed mel bank has %d rows (> 128) at sr=%d", rows, sr);
+            return NCFA_E_OVERFLOW;
+        }
+        std::vector<float> wt((size_t)rows * 32, 0.0f);
+        std::vector<int> lb(4 * 32, 0);
+        for (int q = 0; q < 4; ++q)
+            for (int l = 0; l < 32; ++l) {
+                const int m = mel_band_of(q, l);
+                lb[q * 32 + l] = bin0[m];
+                for (int i = start[m]; i < start[m + 1]; ++i) wt[(size_t)(dt.t.mel_qoff[q] + i - start[m]) * 32 + l] = w[i];
+            }
+        if ((rc = upload(wt, &dt.t.mel_wt))) return rc;
+        if ((rc = upload(lb, &dt.t.mel_lane_bin0))) return rc;
+    }
     if ((rc = upload(hann, &dt.t.hann))) return rc;
     if ((rc = upload(tw1024, &dt.t.tw1024))) return rc;
     if ((rc = upload(tw2048, &dt.t.tw2048))) return rc;

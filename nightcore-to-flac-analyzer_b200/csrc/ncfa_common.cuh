@@ -64,7 +64,15 @@ struct Tables {
     const int *mel_bin0;      // [128] first FFT bin of band m
     int mel_nnz;
     int sr;
+    // lane-transposed mel bank for the warp-per-frame kernels: lane l owns bands l, 63−l, 64+l, 127−l (group q = 0..3);
+    // mel_wt[(mel_qoff[q] + i)·32 + l] = i-th weight of that band (0 beyond its support), i < mel_qw[q]
+    const float *mel_wt;
+    const int *mel_lane_bin0;  // [4][32] first FFT bin of the band of (q, lane)
+    int mel_qoff[4], mel_qw[4], mel_wt_rows;
 };
+__host__ __device__ inline int mel_band_of(int q, int lane) {
+    return q == 0 ? lane : (q == 1 ? 63 - lane : (q == 2 ? 64 + lane : 127 - lane));
+}
 int get_tables(int sr, Tables *out);
 // 127-tap half-band FIR (float64) on the current device (chroma.cu)
 int get_halfband_device(const double **out);

@@ -65,6 +65,56 @@ struct PostStage {
 };
 
 
+// v[n1] = windowed (x[64·n1 + 2·lane], x[64·n1 + 2·lane + 1]) on entry; on return the first 1025 floats of scr
+// hold |X[k]|^2.  tw: [32][32] W_1024 twiddles (shared), scr: per-warp scratch of 32*kScrStride float2.
+__device__ __forceinline__ void warp_power_spectrum_regs(cf (&v)[32], const float2 *tw, float2 *scr, cf twl, int lane) {
+    fft32_dif(v);
+#pragma unroll
+    for (int k1 = 0; k1 < 32; ++k1) {
+        float2 t = tw[k1 * 32 + lane];
+        cf y = cmul(v[br5(k1)], cf{t.x, t.y});
+        scr[k1 * kScrStride + lane] = make_float2(y.x, y.y);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int n2 = 0; n2 < 32; ++n2) {
+        float2 t = scr[lane * kScrStride + n2];
+        v[n2] = cf{t.x, t.y};
+    }
+    __syncwarp();
+    fft32_dif(v);
+    PostStage<0>::run(v, lane, twl, reinterpret_cast<float *>(scr));
+    __syncwarp();
+}
+
+// Frame straight from global memory (L1/L2 serve the overlap between frames): samples x[pos .. pos+2048) of a
+// segment of `len` samples starting at `src`, zeros outside [0, len); hann: 2048 floats (shared).
+__device__ __forceinline__ void warp_power_spectrum_global(const float *__restrict__ src, int64_t pos, int len,
+                                                           const float *hann, const float2 *tw, float2 *scr, cf twl,
+                                                           int lane) {
+    cf v[32];
+    const bool inside = pos >= 0 && pos + 2048 <= (int64_t)len;
+    const float *fr = src + pos;
+    if (inside && ((reinterpret_cast<uintptr_t>(fr) & 7u) == 0)) {
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) {
+            const float2 xs = __ldg(reinterpret_cast<const float2 *>(fr + 64 * n1 + 2 * lane));
+            const float2 ws = *reinterpret_cast<const float2 *>(hann + 64 * n1 + 2 * lane);
+            v[n1] = cf{xs.x * ws.x, xs.y * ws.y};
+        }
+    } else {
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) {
+            const int64_t p = pos + 64 * n1 + 2 * lane;
+            const float x0 = (p >= 0 && p < len) ? __ldg(src + p) : 0.0f;
+            const float x1 = (p + 1 >= 0 && p + 1 < len) ? __ldg(src + p + 1) : 0.0f;
+            const float2 ws = *reinterpret_cast<const float2 *>(hann + 64 * n1 + 2 * lane);
+            v[n1] = cf{x0 * ws.x, x1 * ws.y};
+        }
+    }
+    warp_power_spectrum_regs(v, tw, scr, twl, lane);
+}
+
 // fr: 2048 samples (shared), hann: 2048 (shared), tw: [32][32] W_1024 twiddles (shared),
 // scr: per-warp scratch of 32*kScrStride float2; on return its first 1025 floats hold |X[k]|^2.
 __device__ __forceinline__ void warp_power_spectrum(const float *fr, const float *hann, const float2 *tw, float2 *scr,

@@ -4,100 +4,84 @@
 // Replaces librosa.onset.onset_strength as called at tempo.py:44 (hop 512, one 10 s window per
 // segment) and tempo.py:158 (hop 64, whole track per segment).  SURVEY.md Appendix A.1/A.2.
 //
-// Kernel 1 layout: one CTA of 4 warps owns a tile of FT consecutive frames of one segment.  The
-// overlapping frames are staged once in shared memory; each warp then transforms whole frames:
-// the 2048 real samples are packed as 1024 complex values, lane n2 holds z[32·n1+n2] in
-// registers, runs a 32-point FFT over n1, multiplies by W_1024^(n2·k1), transposes through a
-// padded shared-memory tile, runs the second 32-point FFT, and un-packs the real spectrum with
-// one shuffle per complex value.  The power spectrum goes through shared memory into the
-// sparse mel projection (each lane owns 4 bands).
+// Kernel 1 layout: persistent CTAs, one per SM, 16 warps each; the constant tables (Hann, W_1024 twiddles,
+// lane-transposed mel bank) are staged in shared memory once per CTA.  **One warp = one frame**: the warp
+// loads its 2048 samples straight from global memory (coalesced float2; consecutive frames are handled by
+// the 16 warps of one SM at the same time, so L1 serves the 97 % overlap at hop 64), packs them as 1024
+// complex values (lane n2 holds z[32·n1+n2] in registers), runs a 32-point FFT over n1, multiplies by
+// W_1024^(n2·k1), transposes through a padded per-warp shared tile, runs the second 32-point FFT and
+// un-packs the real spectrum with one shuffle per complex value.  The power spectrum goes through the
+// same per-warp tile into the sparse mel projection (lane owns bands l, 63−l, 64+l, 127−l; weights are
+// stored lane-transposed so the reads are bank-conflict free).  No block-level synchronisation in the loop.
 #include "stft_core.cuh"
 
 namespace ncfa {
 
-constexpr int kWarps = 4;
+constexpr int kWarps = 16;
 constexpr int kThreads = kWarps * 32;
-constexpr int kTileMax = 6144;  // samples staged per CTA
+constexpr int kMelRowsMax = 128;
 
 struct OnsetSmem {
-    float tile[kTileMax];
     float hann[2048];
     float2 tw[1024];
+    float melwt[kMelRowsMax * 32];
+    int lane_bin0[4 * 32];
     float2 scr[kWarps][32 * kScrStride];
-    float melw[2048];
-    int mel_start[NCFA_N_MELS + 1];
-    int mel_bin0[NCFA_N_MELS];
-    float wmax[kWarps];
 };
 
-__host__ __device__ inline int onset_frames_per_tile(int hop) {
-    int ft = (kTileMax - 2048) / hop + 1;
-    ft &= ~3;
-    return ft < 4 ? 4 : (ft > 64 ? 64 : ft);
-}
-
-__global__ void __launch_bounds__(kThreads) stft_logmel_kernel(const float *__restrict__ audio,
-                                                               const int64_t *__restrict__ seg_off,
-                                                               const int32_t *__restrict__ seg_len, int hop,
-                                                               int frames_per_tile, int frame_stride, Tables tb,
-                                                               float *__restrict__ S, unsigned *__restrict__ seg_max) {
+__global__ void __launch_bounds__(kThreads, 1) stft_logmel_kernel(const float *__restrict__ audio,
+                                                                  const int64_t *__restrict__ seg_off,
+                                                                  const int32_t *__restrict__ seg_len, int n_seg,
+                                                                  int hop, int frame_stride, Tables tb,
+                                                                  float *__restrict__ S, unsigned *__restrict__ seg_max) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     OnsetSmem &sm = *reinterpret_cast<OnsetSmem *>(smem_raw);
-    const int seg = blockIdx.y;
-    const int len = seg_len[seg];
-    const int n_frames = 1 + len / hop;
-    const int f0 = blockIdx.x * frames_per_tile;
-    if (f0 >= n_frames) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float *src = audio + seg_off[seg];
-
-    // ---- stage constants and the sample tile
     for (int i = tid; i < 2048; i += kThreads) sm.hann[i] = tb.hann[i];
     for (int i = tid; i < 1024; i += kThreads) sm.tw[i] = tb.tw1024[i];
-    for (int i = tid; i < tb.mel_nnz; i += kThreads) sm.melw[i] = tb.mel_w[i];
-    for (int i = tid; i <= NCFA_N_MELS; i += kThreads) sm.mel_start[i] = tb.mel_start[i];
-    for (int i = tid; i < NCFA_N_MELS; i += kThreads) sm.mel_bin0[i] = tb.mel_bin0[i];
-    const int nf_tile = min(frames_per_tile, n_frames - f0);
-    const int tile_n = (nf_tile - 1) * hop + 2048;
-    const int64_t pos0 = (int64_t)f0 * hop - 1024;  // sample index of tile[0]
-    for (int i = tid; i < tile_n; i += kThreads) {
-        int64_t p = pos0 + i;
-        sm.tile[i] = (p >= 0 && p < len) ? __ldg(src + p) : 0.0f;
-    }
+    for (int i = tid; i < tb.mel_wt_rows * 32; i += kThreads) sm.melwt[i] = tb.mel_wt[i];
+    for (int i = tid; i < 4 * 32; i += kThreads) sm.lane_bin0[i] = tb.mel_lane_bin0[i];
     __syncthreads();
 
     const cf twl = cf{tb.tw2048[lane].x, tb.tw2048[lane].y};
     float2 *scr = sm.scr[warp];
-    float *pw = reinterpret_cast<float *>(scr);
-    float vmax = -INFINITY;
+    const float *pw = reinterpret_cast<const float *>(scr);
+    int b0[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) b0[q] = sm.lane_bin0[q * 32 + lane];
+    const int64_t total = (int64_t)n_seg * frame_stride;
+    int cur_seg = -1;
+    float cur_max = -INFINITY;
+    // items (seg, frame) are dealt in groups of kWarps consecutive frames per CTA
+    for (int64_t item = (int64_t)blockIdx.x * kWarps + warp; item < total; item += (int64_t)gridDim.x * kWarps) {
+        const int seg = (int)(item / frame_stride);
+        const int frame = (int)(item - (int64_t)seg * frame_stride);
+        const int len = seg_len[seg];
+        if (frame >= 1 + len / hop) continue;
+        if (seg != cur_seg) {
+            if (cur_seg >= 0 && lane == 0) atomicMax(seg_max + cur_seg, float_to_ordered(cur_max));
+            cur_seg = seg;
+            cur_max = -INFINITY;
+        }
+        warp_power_spectrum_global(audio + seg_off[seg], (int64_t)frame * hop - 1024, len, sm.hann, sm.tw, scr, twl, lane);
 
-    for (int fl = warp; fl < nf_tile; fl += kWarps) {
-        warp_power_spectrum(sm.tile + fl * hop, sm.hann, sm.tw, scr, twl, lane);
-
-        // sparse mel projection: lane owns bands lane, 63-lane, 64+lane, 127-lane
-        const int frame = f0 + fl;
         float *Sout = S + ((size_t)seg * frame_stride + frame) * NCFA_N_MELS;
+        float vmax = -INFINITY;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const int band = (q == 0) ? lane : (q == 1) ? 63 - lane : (q == 2) ? 64 + lane : 127 - lane;
-            const int s = sm.mel_start[band], e = sm.mel_start[band + 1];
-            const float *pk = pw + sm.mel_bin0[band];
+            const float *wt = sm.melwt + (size_t)tb.mel_qoff[q] * 32 + lane;
+            const float *pk = pw + b0[q];
+            const int nw = tb.mel_qw[q];
             float acc = 0.0f;
-            for (int i = s; i < e; ++i) acc = fmaf(sm.melw[i], pk[i - s], acc);
-            float db = 10.0f * log10f(fmaxf(1e-10f, acc));
-            Sout[band] = db;
+            for (int i = 0; i < nw; ++i) acc = fmaf(wt[i * 32], pk[i], acc);  // zero weights beyond the band's support
+            const float db = 10.0f * log10f(fmaxf(1e-10f, acc));
+            Sout[mel_band_of(q, lane)] = db;
             vmax = fmaxf(vmax, db);
         }
+        cur_max = fmaxf(cur_max, warp_max(vmax));
         __syncwarp();
     }
-    vmax = warp_max(vmax);
-    if (lane == 0) sm.wmax[warp] = vmax;
-    __syncthreads();
-    if (tid == 0) {
-        float m = sm.wmax[0];
-        for (int w = 1; w < kWarps; ++w) m = fmaxf(m, sm.wmax[w]);
-        atomicMax(seg_max + seg, float_to_ordered(m));
-    }
+    if (cur_seg >= 0 && lane == 0) atomicMax(seg_max + cur_seg, float_to_ordered(cur_max));
 }
 
 // onset[j] = 0 for j < pad;  else mean_m relu(clamp(S[j-pad+1][m]) - clamp(S[j-pad][m]))
@@ -159,18 +143,22 @@ extern "C" int ncfa_onset_strength_batched(const float *d_audio, const int64_t *
     float *S = (float *)d_workspace;
     unsigned *seg_max = (unsigned *)((char *)d_workspace + align_up((size_t)n_seg * frames * NCFA_N_MELS * 4, 256));
     NCFA_CUDA_OK(cudaMemsetAsync(seg_max, 0, (size_t)n_seg * 4, st));
-    const int ft = onset_frames_per_tile(hop);
     static bool attr_done = false;
+    static int n_sm = 0;
     if (!attr_done) {
         NCFA_CUDA_OK(cudaFuncSetAttribute(stft_logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)sizeof(OnsetSmem)));
+        int dev = 0;
+        NCFA_CUDA_OK(cudaGetDevice(&dev));
+        NCFA_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         attr_done = true;
     }
-    dim3 g1((frames + ft - 1) / ft, n_seg);
     {
+        const int64_t groups = ((int64_t)n_seg * frames + kWarps - 1) / kWarps;
+        const int grid = (int)(groups < n_sm ? groups : n_sm);  // persistent: one CTA per SM
         ProfScope _p("stft_logmel_kernel", st);
-        stft_logmel_kernel<<<g1, kThreads, sizeof(OnsetSmem), st>>>(d_audio, d_seg_off, d_seg_len, hop, ft, frames, tb, S,
-                                                                seg_max);
+        stft_logmel_kernel<<<grid, kThreads, sizeof(OnsetSmem), st>>>(d_audio, d_seg_off, d_seg_len, n_seg, hop, frames, tb,
+                                                                  S, seg_max);
     }
     NCFA_LAUNCH_OK("stft_logmel_kernel");
     const int pad = 1 + NCFA_N_FFT / (2 * hop);
