@@ -15,12 +15,15 @@
 //   chroma_mean_kernel    partial sums → mean chroma float64[12] per segment
 //   cyclic_xcorr_kernel   argmax_k dot(src, roll(nc, −k)) wrapped to (−n/2, n/2]
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <algorithm>
 #include <complex>
 #include <map>
 #include <mutex>
 #include <vector>
 #include "stft_core.cuh"
+#include "tc05.cuh"
 
 namespace ncfa {
 
@@ -36,7 +39,37 @@ constexpr int kPeakStride = 180;  // ≥ max local maxima among the 358 candidat
 struct ChromaTables {
     const float *K;     // [100][1024][72]  K[j][n][r]: r < 36 real part of bin r, r ≥ 36 imaginary part of bin r−36
     const double *hb;   // [127] half-band taps
+    const float *Bimg;  // [100][32 k-tiles][hi, lo][80 rows × 32 k] tf32 split of K as swizzle-128B shared-memory images
 };
+
+constexpr int kTcN = 80;                          // MMA N: 72 rows of K + 8 zero rows (N % 16 == 0 for M = 128)
+constexpr int kTcKT = 32;                         // k (time-sample) tile = one 128-byte swizzle row of tf32
+constexpr int kTcBTileBytes = kTcN * kTcKT * 4;   // 10240: one of {hi, lo}
+constexpr int kTcBStageBytes = 2 * kTcBTileBytes; // hi then lo
+
+static float host_tf32_rna(float x) {  // cvt.rna.tf32.f32: nearest, ties away from zero, low 13 mantissa bits cleared
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    u = (u + 0x1000u) & ~0x1FFFu;
+    float r;
+    memcpy(&r, &u, 4);
+    return r;
+}
+
+// K[1024][72] of one tuning → 32 stage images; element (row r, k c) of a tile lives at
+// (r/8)·1024 + (r%8)·128 + ((c/4) ^ (r%8))·16 + (c%4)·4   (Swizzle<3,4,3> on a 1024-byte aligned tile)
+static void build_b_image(const float *K, float *img /* [32][2][80*32] */) {
+    for (int kt = 0; kt < kCqtNfft / kTcKT; ++kt)
+        for (int r = 0; r < kTcN; ++r)
+            for (int c = 0; c < kTcKT; ++c) {
+                const float x = r < kCqtRows ? K[(size_t)(kt * kTcKT + c) * kCqtRows + r] : 0.0f;
+                const float hi = host_tf32_rna(x), lo = x - hi;
+                const size_t off = ((size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128 + (size_t)(((c >> 2) ^ (r & 7)) * 16) +
+                                    (size_t)(c & 3) * 4) / 4;
+                img[((size_t)kt * 2 + 0) * (kTcN * kTcKT) + off] = hi;
+                img[((size_t)kt * 2 + 1) * (kTcN * kTcKT) + off] = lo;
+            }
+}
 
 // ------------------------------------------------------------------------------------------------ host tables
 static void fft_inplace(std::vector<std::complex<double>> &a) {
@@ -212,6 +245,16 @@ static int get_chroma_tables(int sr, ChromaTables *out) {
     {
         int rc = get_halfband_device(&t.hb);
         if (rc) return rc;
+    }
+    {
+        const size_t per = (size_t)(kCqtNfft / kTcKT) * 2 * kTcN * kTcKT;
+        std::vector<float> img((size_t)kNTunings * per);
+        for (int j = 0; j < kNTunings; ++j)
+            build_b_image(all.data() + (size_t)j * kCqtNfft * kCqtRows, img.data() + (size_t)j * per);
+        float *dB = nullptr;
+        NCFA_CUDA_OK(cudaMalloc(&dB, img.size() * sizeof(float)));
+        NCFA_CUDA_OK(cudaMemcpy(dB, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice));
+        t.Bimg = dB;
     }
     t.K = dK;
     g_chroma_tables[key] = t;
@@ -590,13 +633,252 @@ __global__ void __launch_bounds__(kCqtThreads) cqt_chroma_kernel(const float *__
     }
 }
 
+// ------------------------------------------------------------------------------------------------ CQT on tcgen05
+// Same contraction on the 5th-generation tensor cores:  D[128 frames × 80] (+)= A[128 × 8]·B[80 × 8]^T, kind::tf32,
+// with the 3×TF32 split  x = hi + lo  (hi = rna_tf32(x), lo = x − hi exactly):  A·B ≈ Ah·Bh + Al·Bh + Ah·Bl.
+//   A (the Hankel matrix of frames) is never materialised in memory: frame thread f keeps row f, reads its 32 samples of
+//     the k-tile straight from global memory (L1/L2 serve the overlap between frames), splits them in registers and
+//     writes hi / lo into TENSOR MEMORY with tcgen05.st; the MMA reads A from TMEM (TS form).
+//   B (the folded CQT matrix) is pre-split and pre-swizzled on the host as shared-memory images, so a k-tile is ONE
+//     20 KB 1-D bulk async copy (cp.async.bulk + mbarrier complete_tx) — no tensor map needed.
+//   D lives in TMEM, double buffered across octaves; the epilogue (tcgen05.ld → |re + i·im| → fold to 12 chroma) of
+//     octave o−1 overlaps the MMAs of octave o.
+// Warp roles (192 threads): warps 0-3 frame warps (A producer + epilogue, TMEM lanes 32w..32w+31), warp 4 MMA issuer
+// (one lane) and TMEM allocator, warp 5 B loader (one lane).  Pipelines: A ring (4 stages in TMEM), B ring (6 stages in
+// shared memory), accumulator ring (2).
+constexpr int kTcFrames = 128;
+constexpr int kTcThreads = 192;
+constexpr int kTcAStages = 4;
+constexpr int kTcBStages = 6;
+constexpr int kTcACols = 2 * kTcKT;                      // hi + lo columns of one A stage
+constexpr int kTcAccCol0 = kTcAStages * kTcACols;        // 256
+constexpr int kTcTmemCols = 512;                         // 256 (A ring) + 2 × 80 (accumulators) → next power of two
+
+struct TcSmem {
+    alignas(1024) unsigned char b[kTcBStages][kTcBStageBytes];
+    alignas(8) uint64_t full_a[kTcAStages], empty_a[kTcAStages], full_b[kTcBStages], empty_b[kTcBStages];
+    uint64_t acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+    double red[4][kChroma];
+};
+
+__device__ __forceinline__ void tc_load_row32(const float *__restrict__ y, int64_t pos, int len, float (&x)[32]) {
+    if (pos >= 0 && pos + 32 <= (int64_t)len && ((reinterpret_cast<uintptr_t>(y + pos) & 15u) == 0)) {
+        const float4 *p = reinterpret_cast<const float4 *>(y + pos);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 v = __ldg(p + i);
+            x[4 * i] = v.x;
+            x[4 * i + 1] = v.y;
+            x[4 * i + 2] = v.z;
+            x[4 * i + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int64_t q = pos + i;
+            x[i] = (q >= 0 && q < len) ? __ldg(y + q) : 0.0f;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__restrict__ audio,
+                                                               const int64_t *__restrict__ seg_off,
+                                                               const int32_t *__restrict__ seg_len,
+                                                               const float *__restrict__ pyr, PyrOffsets po,
+                                                               const int32_t *__restrict__ tuning_idx,
+                                                               const float *__restrict__ Bimg, int tile_stride,
+                                                               double *__restrict__ partial) {
+    using namespace tc05;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    TcSmem &sm = *reinterpret_cast<TcSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int seg = blockIdx.y;
+    const int n = seg_len[seg];
+    const int n_frames = cqt_frames(n);
+    const int t0 = blockIdx.x * kTcFrames;
+    if (t0 >= n_frames) return;  // whole CTA leaves before any barrier / TMEM state exists
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int i = 0; i < kTcAStages; ++i) {
+            mbar_init(&sm.full_a[i], kTcFrames);
+            mbar_init(&sm.empty_a[i], 1);
+        }
+        for (int i = 0; i < kTcBStages; ++i) {
+            mbar_init(&sm.full_b[i], 1);
+            mbar_init(&sm.empty_b[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&sm.acc_full[i], 1);
+            mbar_init(&sm.acc_empty[i], kTcFrames);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 4) tmem_alloc(&sm.tmem_base, kTcTmemCols);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = sm.tmem_base;
+
+    int tj = tuning_idx[seg];
+    tj = tj < 0 ? 0 : (tj >= kNTunings ? kNTunings - 1 : tj);
+    constexpr int kKTiles = kCqtNfft / kTcKT;  // 32
+    constexpr int kIters = kOctaves * kKTiles;
+
+    if (warp < 4) {
+        // ===================== frame warps: A producer + epilogue =====================
+        const int f = tid;  // row of the tile = TMEM lane
+        const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
+        const float *pseg = pyr + (size_t)seg * po.off[kOctaves];
+        float chroma[kChroma];
+#pragma unroll
+        for (int c = 0; c < kChroma; ++c) chroma[c] = 0.0f;
+
+        auto epilogue = [&](int o) {
+            const int buf = o & 1;
+            mbar_wait(&sm.acc_full[buf], (uint32_t)((o >> 1) & 1));
+            fence_after_sync();
+            float re[kCqtBins];
+            // columns 0..35 real parts, 36..71 imaginary parts
+            uint32_t v[16];
+            const uint32_t acc = tmem + lane_base + (uint32_t)(kTcAccCol0 + buf * kTcN);
+            float im[kCqtBins];
+#pragma unroll
+            for (int g = 0; g < 5; ++g) {
+                tmem_ld16(acc + 16 * g, v);
+                wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int col = 16 * g + i;
+                    if (col < kCqtBins) re[col] = __uint_as_float(v[i]);
+                    else if (col < 2 * kCqtBins) im[col - kCqtBins] = __uint_as_float(v[i]);
+                }
+            }
+            fence_before_sync();
+            mbar_arrive(&sm.acc_empty[buf]);
+#pragma unroll
+            for (int b = 0; b < kCqtBins; ++b) {
+                const float m = sqrtf(re[b] * re[b] + im[b] * im[b]);
+                chroma[((b + 1) % kCqtBins) / 3] += m;  // cq_to_chroma: 3 bins per semitone, rolled −1
+            }
+        };
+
+        for (int o = 0; o < kOctaves; ++o) {
+            const int hop = 512 >> o;
+            const float *y = (o == 0) ? audio + seg_off[seg] : pseg + po.off[o];
+            const int len = level_len(n, o);
+            const int64_t row0 = (int64_t)(t0 + f) * hop - kCqtNfft / 2;
+            float x[32];
+            tc_load_row32(y, row0, len, x);
+            for (int kt = 0; kt < kKTiles; ++kt) {
+                const int it = o * kKTiles + kt;
+                const int st = it % kTcAStages;
+                float xn[32];
+                if (kt + 1 < kKTiles) tc_load_row32(y, row0 + (int64_t)(kt + 1) * kTcKT, len, xn);  // prefetch
+                mbar_wait(&sm.empty_a[st], (uint32_t)(((it / kTcAStages) & 1) ^ 1));
+                fence_after_sync();
+                const uint32_t a0 = tmem + lane_base + (uint32_t)(st * kTcACols);
+                uint32_t h[16], l[16];
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float xv = x[16 * half + i];
+                        const float hi = to_tf32(xv);
+                        h[i] = __float_as_uint(hi);
+                        l[i] = __float_as_uint(xv - hi);
+                    }
+                    tmem_st16(a0 + 16 * half, h);
+                    tmem_st16(a0 + kTcKT + 16 * half, l);
+                }
+                wait_st();
+                fence_before_sync();
+                mbar_arrive(&sm.full_a[st]);
+                if (kt + 1 < kKTiles) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) x[i] = xn[i];
+                }
+            }
+            if (o > 0) epilogue(o - 1);
+        }
+        epilogue(kOctaves - 1);
+
+        // ---- librosa.util.normalize(norm=inf) per frame, then the tile's sum over frames (float64)
+        const bool valid = (t0 + f) < n_frames;
+        float mx = 0.0f;
+#pragma unroll
+        for (int c = 0; c < kChroma; ++c) mx = fmaxf(mx, chroma[c]);
+        const double len_ = (mx < 1.17549435e-38f) ? 1.0 : (double)mx;
+#pragma unroll
+        for (int c = 0; c < kChroma; ++c) {
+            double v = valid ? (double)chroma[c] / len_ : 0.0;
+            v = warp_sum(v);
+            if (lane == 0) sm.red[warp][c] = v;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four frame warps only
+        if (tid < kChroma)
+            partial[((size_t)seg * tile_stride + blockIdx.x) * kChroma + tid] =
+                ((sm.red[0][tid] + sm.red[1][tid]) + sm.red[2][tid]) + sm.red[3][tid];
+    } else if (warp == 4) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = idesc_tf32(kTcFrames, kTcN);
+            for (int o = 0; o < kOctaves; ++o) {
+                const int buf = o & 1;
+                mbar_wait(&sm.acc_empty[buf], (uint32_t)(((o >> 1) & 1) ^ 1));
+                fence_after_sync();
+                const uint32_t d = tmem + (uint32_t)(kTcAccCol0 + buf * kTcN);
+                for (int kt = 0; kt < kKTiles; ++kt) {
+                    const int it = o * kKTiles + kt;
+                    const int sa = it % kTcAStages, sb = it % kTcBStages;
+                    mbar_wait(&sm.full_a[sa], (uint32_t)((it / kTcAStages) & 1));
+                    mbar_wait(&sm.full_b[sb], (uint32_t)((it / kTcBStages) & 1));
+                    fence_after_sync();
+                    const uint64_t bh = smem_desc_k128(sm.b[sb]);
+                    const uint64_t bl = smem_desc_k128(sm.b[sb] + kTcBTileBytes);
+                    const uint32_t ah = tmem + (uint32_t)(sa * kTcACols), al = ah + kTcKT;
+#pragma unroll
+                    for (int k = 0; k < kTcKT / 8; ++k) {
+                        const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 32 bytes per K = 8 step inside the swizzle row
+                        mma_tf32_ts(d, ah + 8 * k, bh + adv, idesc, (kt | k) != 0);
+                        mma_tf32_ts(d, al + 8 * k, bh + adv, idesc, 1);
+                        mma_tf32_ts(d, ah + 8 * k, bl + adv, idesc, 1);
+                    }
+                    commit(&sm.empty_a[sa]);
+                    commit(&sm.empty_b[sb]);
+                }
+                commit(&sm.acc_full[buf]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== B loader =====================
+        if (lane == 0) {
+            const unsigned char *src = reinterpret_cast<const unsigned char *>(Bimg) + (size_t)tj * kKTiles * kTcBStageBytes;
+            for (int it = 0; it < kIters; ++it) {
+                const int sb = it % kTcBStages, kt = it % kKTiles;
+                mbar_wait(&sm.empty_b[sb], (uint32_t)(((it / kTcBStages) & 1) ^ 1));
+                mbar_arrive_expect_tx(&sm.full_b[sb], kTcBStageBytes);
+                bulk_g2s(sm.b[sb], src + (size_t)kt * kTcBStageBytes, kTcBStageBytes, &sm.full_b[sb]);
+            }
+        }
+        __syncwarp();
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 4) {
+        fence_after_sync();
+        tmem_dealloc(tmem, kTcTmemCols);
+    }
+}
+
 // mean over frames: one warp per segment sums the tile partials in tile order
 __global__ void __launch_bounds__(32) chroma_mean_kernel(const int32_t *__restrict__ seg_len, int tile_stride,
-                                                         const double *__restrict__ partial,
+                                                         int frames_per_tile, const double *__restrict__ partial,
                                                          double *__restrict__ chroma) {
     const int seg = blockIdx.x;
     const int n_frames = cqt_frames(seg_len[seg]);
-    const int n_tiles = (n_frames + kCqtTF - 1) / kCqtTF;
+    const int n_tiles = (n_frames + frames_per_tile - 1) / frames_per_tile;
     const int ch = threadIdx.x;
     if (ch >= kChroma) return;
     double s = 0.0;
@@ -739,23 +1021,37 @@ extern "C" int ncfa_chroma_mean_batched(const float *d_audio, const int64_t *d_s
                                             level >= 2 ? po.off[level - 1] : 0, po.off[level], ct.hb);
         NCFA_LAUNCH_OK("decimate2_kernel");
     }
+    // NCFA_CQT_IMPL=simt selects the CUDA-core contraction (kept as the cross-check of the tensor-core kernel)
+    static int use_tc = -1;
+    if (use_tc < 0) {
+        const char *e = getenv("NCFA_CQT_IMPL");
+        use_tc = (e && strcmp(e, "simt") == 0) ? 0 : 1;
+    }
     static bool attr_done = false;
     if (!attr_done) {
         NCFA_CUDA_OK(cudaFuncSetAttribute(cqt_chroma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)sizeof(CqtSmem)));
+        NCFA_CUDA_OK(cudaFuncSetAttribute(cqt_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(TcSmem) + 1024));
         attr_done = true;
     }
-    const int tiles = chroma_tiles(max_seg_len);
-    {
+    const int tiles = chroma_tiles(max_seg_len);  // partial[] stride (sized for the 32-frame tiles of the SIMT kernel)
+    if (use_tc) {
+        ProfScope _p("cqt_tc_kernel", st);
+        dim3 g((cqt_frames(max_seg_len) + kTcFrames - 1) / kTcFrames, n_seg);
+        cqt_tc_kernel<<<g, kTcThreads, sizeof(TcSmem) + 1024, st>>>(d_audio, d_seg_off, d_seg_len, pyr, po, d_tuning_idx,
+                                                                    ct.Bimg, tiles, partial);
+        NCFA_LAUNCH_OK("cqt_tc_kernel");
+    } else {
         ProfScope _p("cqt_chroma_kernel", st);
         dim3 g(tiles, n_seg);
         cqt_chroma_kernel<<<g, kCqtThreads, sizeof(CqtSmem), st>>>(d_audio, d_seg_off, d_seg_len, pyr, po, d_tuning_idx,
                                                                     ct.K, tiles, partial);
+        NCFA_LAUNCH_OK("cqt_chroma_kernel");
     }
-    NCFA_LAUNCH_OK("cqt_chroma_kernel");
     {
         ProfScope _p("chroma_mean_kernel", st);
-        chroma_mean_kernel<<<n_seg, 32, 0, st>>>(d_seg_len, tiles, partial, d_chroma);
+        chroma_mean_kernel<<<n_seg, 32, 0, st>>>(d_seg_len, tiles, use_tc ? kTcFrames : kCqtTF, partial, d_chroma);
     }
     NCFA_LAUNCH_OK("chroma_mean_kernel");
     return NCFA_OK;
