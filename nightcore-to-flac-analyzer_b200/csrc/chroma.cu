@@ -451,36 +451,66 @@ __global__ void __launch_bounds__(256) tuning_pick_kernel(const int32_t *__restr
 }
 
 // ------------------------------------------------------------------------------------------------ decimation
-// out[i] = float32( √2 · Σ_k h[k]·in[2i + k − 63] ),  n_out = ceil(n_in / 2)
+// out[t] = float32( √2 · Σ_k h[k]·in[2t + k − 63] ),  n_out = ceil(n_in / 2).
+// Half-band structure: besides the centre tap only the even-indexed taps are non-zero (the others are sin(mπ)
+// rounding residue below 1e-17 and are skipped), and they all hit ODD input samples:
+//     out[t] = h[63]·xe[t] + Σ_{m<64} h[2m]·xo[t + m − 32],   xe[j] = in[2j], xo[j] = in[2j+1].
+// A CTA de-interleaves its input span into xe / xo in shared memory; each thread produces 4 consecutive outputs
+// from a 67-sample register window (17 conflict-free LDS.128), float64 accumulation.
+constexpr int kDecOutPerCta = 1024;
 __global__ void __launch_bounds__(256) decimate2_kernel(const float *__restrict__ audio,
                                                         const int64_t *__restrict__ seg_off,
                                                         const int32_t *__restrict__ seg_len, int level,
                                                         float *__restrict__ pyr, size_t pyr_stride, size_t in_off,
                                                         size_t out_off, const double *__restrict__ hb) {
-    __shared__ double h[kHbTaps];
-    __shared__ float xin[2 * 256 + kHbTaps - 1];
+    __shared__ double h_even[64];
+    __shared__ double h_mid;
+    __shared__ __align__(16) float xo[kDecOutPerCta + 64 + 4];
+    __shared__ __align__(16) float xe[kDecOutPerCta];
     const int seg = blockIdx.y;
     const int n0 = seg_len[seg];
     const int n_in = level_len(n0, level - 1), n_out = (n_in + 1) >> 1;
-    const int i0 = blockIdx.x * 256;
-    if (i0 >= n_out) return;
+    const int o0 = blockIdx.x * kDecOutPerCta;
+    if (o0 >= n_out) return;
     const float *in = (level == 1) ? audio + seg_off[seg] : pyr + (size_t)seg * pyr_stride + in_off;
     float *out = pyr + (size_t)seg * pyr_stride + out_off;
-    for (int i = threadIdx.x; i < kHbTaps; i += 256) h[i] = hb[i];
-    const int base = 2 * i0 - (kHbTaps - 1) / 2;
-    for (int i = threadIdx.x; i < 2 * 256 + kHbTaps - 1; i += 256) {
-        const int p = base + i;
-        xin[i] = (p >= 0 && p < n_in) ? __ldg(in + p) : 0.0f;
+    if (threadIdx.x < 64) h_even[threadIdx.x] = hb[2 * threadIdx.x];
+    if (threadIdx.x == 64) h_mid = hb[(kHbTaps - 1) / 2];
+    // xo[i] = in[2(o0 − 32 + i) + 1], i < 1024 + 64 + 4;  xe[i] = in[2(o0 + i)], i < 1024
+    for (int i = threadIdx.x; i < kDecOutPerCta + 64 + 4; i += 256) {
+        const int64_t p = 2 * ((int64_t)o0 - 32 + i) + 1;
+        xo[i] = (p >= 0 && p < n_in) ? __ldg(in + p) : 0.0f;
+    }
+    for (int i = threadIdx.x; i < kDecOutPerCta; i += 256) {
+        const int64_t p = 2 * ((int64_t)o0 + i);
+        xe[i] = (p < n_in) ? __ldg(in + p) : 0.0f;
     }
     __syncthreads();
-    const int i = i0 + threadIdx.x;
-    if (i >= n_out) return;
-    // half-band: the taps at odd offsets from the centre are the only non-zero ones besides the centre itself
-    // (the others are sin(mπ)-rounding residue below 1e-17 and are skipped)
-    double acc = h[(kHbTaps - 1) / 2] * (double)xin[2 * threadIdx.x + (kHbTaps - 1) / 2];
-#pragma unroll 8
-    for (int k = 0; k < kHbTaps; k += 2) acc = fma(h[k], (double)xin[2 * threadIdx.x + k], acc);
-    out[i] = (float)(acc * 1.4142135623730951);
+    const int t = 4 * threadIdx.x;  // outputs o0 + t .. o0 + t + 3 use xo[t .. t + 66]
+    float w[68];
+#pragma unroll
+    for (int j = 0; j < 17; ++j) {
+        const float4 v = *reinterpret_cast<const float4 *>(xo + t + 4 * j);
+        w[4 * j] = v.x;
+        w[4 * j + 1] = v.y;
+        w[4 * j + 2] = v.z;
+        w[4 * j + 3] = v.w;
+    }
+    const float4 e = *reinterpret_cast<const float4 *>(xe + t);
+    double a0 = h_mid * (double)e.x, a1 = h_mid * (double)e.y, a2 = h_mid * (double)e.z, a3 = h_mid * (double)e.w;
+#pragma unroll
+    for (int m = 0; m < 64; ++m) {
+        const double hm = h_even[m];
+        a0 = fma(hm, (double)w[m], a0);
+        a1 = fma(hm, (double)w[m + 1], a1);
+        a2 = fma(hm, (double)w[m + 2], a2);
+        a3 = fma(hm, (double)w[m + 3], a3);
+    }
+    const int o = o0 + t;
+    if (o < n_out) out[o] = (float)(a0 * 1.4142135623730951);
+    if (o + 1 < n_out) out[o + 1] = (float)(a1 * 1.4142135623730951);
+    if (o + 2 < n_out) out[o + 2] = (float)(a2 * 1.4142135623730951);
+    if (o + 3 < n_out) out[o + 3] = (float)(a3 * 1.4142135623730951);
 }
 
 // ------------------------------------------------------------------------------------------------ CQT → chroma
@@ -1016,7 +1046,7 @@ extern "C" int ncfa_chroma_mean_batched(const float *d_audio, const int64_t *d_s
         const int n_out = level_len(max_seg_len, level);
         if (n_out <= 0) continue;
         ProfScope _p("decimate2_kernel", st);
-        dim3 g((n_out + 255) / 256, n_seg);
+        dim3 g((n_out + kDecOutPerCta - 1) / kDecOutPerCta, n_seg);
         decimate2_kernel<<<g, 256, 0, st>>>(d_audio, d_seg_off, d_seg_len, level, pyr, stride,
                                             level >= 2 ? po.off[level - 1] : 0, po.off[level], ct.hb);
         NCFA_LAUNCH_OK("decimate2_kernel");

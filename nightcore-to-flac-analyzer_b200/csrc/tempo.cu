@@ -43,28 +43,70 @@ __global__ void tg_tables_kernel(int W, double2 *__restrict__ trig, double *__re
     w2[j] = w * w;
 }
 
-// pass 1: r0[seg][t] = Σ_j w2[j]·x[t+j]^2
-__global__ void __launch_bounds__(256) tg_r0_kernel(const float *__restrict__ onset, const int64_t *__restrict__ onset_off,
-                                                    const int32_t *__restrict__ env_len, int env_stride, int W,
-                                                    const double *__restrict__ w2, double *__restrict__ r0) {
-    extern __shared__ double xs[];  // 256 + W
+// pass 1: r0[seg][t] = Σ_j w[j]²·x[t+j]²  — the lag-0 autocorrelation every frame is normalised by.
+// w² = 3/8 − ½cos θj + ⅛cos 2θj, so r0 = ⅜S0 − ½Re S1 + ⅛Re S2 with the same three running sums as the lags
+// (L = W): one thread owns kR0Block consecutive frames, sums them exactly at the first one and slides; whenever
+// the combination cancels (r0 below 1e-3 of its S0 part) the frame is re-summed directly with the w² table.
+constexpr int kR0Block = 128;
+constexpr int kR0Threads = 64;
+__device__ __forceinline__ int r0_pad(int i) { return i + (i >> 5); }  // spreads the per-thread streams over banks
+
+__global__ void __launch_bounds__(kR0Threads) tg_r0_kernel(const float *__restrict__ onset,
+                                                           const int64_t *__restrict__ onset_off,
+                                                           const int32_t *__restrict__ env_len, int env_stride, int W,
+                                                           const double2 *__restrict__ trig,
+                                                           const double *__restrict__ w2, double *__restrict__ r0) {
+    extern __shared__ double zs[];  // r0_pad(kR0Threads·kR0Block + W) squared padded-envelope samples
     const int seg = blockIdx.y;
     const int n = env_len[seg];
-    const int t0 = blockIdx.x * 256;
-    if (t0 >= n) return;
+    const int f0 = blockIdx.x * (kR0Threads * kR0Block);
+    if (f0 >= n) return;
     const float *on = onset + onset_off[seg];
     const int p = W / 2;
-    const int span = min(256, n - t0) + W - 1;
-    for (int i = threadIdx.x; i < span; i += 256) {
-        double v = padded_env(on, n, p, t0 + i);
-        xs[i] = v * v;
+    const int span = min(kR0Threads * kR0Block, n - f0) + W;
+    for (int i = threadIdx.x; i < span; i += kR0Threads) {
+        const int m = f0 + i;
+        const double v = (m < n + 2 * p) ? padded_env(on, n, p, m) : 0.0;
+        zs[r0_pad(i)] = v * v;
     }
     __syncthreads();
-    const int t = t0 + threadIdx.x;
-    if (t >= n) return;
-    double acc = 0.0;
-    for (int j = 0; j < W; ++j) acc = fma(__ldg(w2 + j), xs[threadIdx.x + j], acc);
-    r0[(size_t)seg * env_stride + t] = acc;
+    const int tb = f0 + threadIdx.x * kR0Block;
+    if (tb >= n) return;
+    const int te = min(n, tb + kR0Block);
+    const int o0 = tb - f0;
+    double S0 = 0, S1r = 0, S1i = 0, S2r = 0, S2i = 0;
+    for (int j = 0; j < W; ++j) {
+        const double z = zs[r0_pad(o0 + j)];
+        const double2 a = trig[j];
+        int j2 = 2 * j;
+        if (j2 >= W) j2 -= W;
+        const double2 b = trig[j2];
+        S0 += z;
+        S1r = fma(z, a.x, S1r);
+        S1i = fma(z, a.y, S1i);
+        S2r = fma(z, b.x, S2r);
+        S2i = fma(z, b.y, S2i);
+    }
+    const double2 e1 = trig[1 % W], e2 = trig[2 % W];
+    double *out = r0 + (size_t)seg * env_stride;
+    for (int t = tb; t < te; ++t) {
+        const int o = t - f0;
+        double r = 0.375 * S0 - 0.5 * S1r + 0.125 * S2r;
+        if (!(r >= 1e-3 * (0.375 * S0))) {  // cancellation (or NaN): exact direct sum for this frame
+            r = 0.0;
+            for (int j = 0; j < W; ++j) r = fma(__ldg(w2 + j), zs[r0_pad(o + j)], r);
+        }
+        out[t] = r;
+        if (t + 1 < te) {
+            const double d = zs[r0_pad(o + W)] - zs[r0_pad(o)];  // e^{iθW} = 1: the entering sample has phase 0 after the shift
+            S0 += d;
+            const double a1 = S1r + d, a2 = S2r + d;
+            S1r = a1 * e1.x + S1i * e1.y;
+            S1i = S1i * e1.x - a1 * e1.y;
+            S2r = a2 * e2.x + S2i * e2.y;
+            S2i = S2i * e2.x - a2 * e2.y;
+        }
+    }
 }
 
 // pass 2: partial[seg][chunk][k] = Σ_{t in chunk} R_t[k] / R_t[0]
@@ -350,11 +392,18 @@ extern "C" int ncfa_tempo_lag_batched(const float *d_onset, const int64_t *d_ons
     }
     NCFA_LAUNCH_OK("tg_tables_kernel");
     {
-        dim3 g((max_env_len + 255) / 256, n_seg);
-        size_t sh = (size_t)(256 + W) * 8;
+        const int per_cta = kR0Threads * kR0Block;
+        dim3 g((max_env_len + per_cta - 1) / per_cta, n_seg);
+        const int span_max = (max_env_len < per_cta ? max_env_len : per_cta) + W;
+        size_t sh = (size_t)(span_max + (span_max >> 5) + 2) * 8;
+        static size_t sh_set0 = 0;
+        if (sh > 48 * 1024 && sh > sh_set0) {
+            NCFA_CUDA_OK(cudaFuncSetAttribute(tg_r0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+            sh_set0 = sh;
+        }
         {
             ProfScope _p("tg_r0_kernel", st);
-            tg_r0_kernel<<<g, 256, sh, st>>>(d_onset, d_onset_off, d_env_len, max_env_len, W, w2, r0);
+            tg_r0_kernel<<<g, kR0Threads, sh, st>>>(d_onset, d_onset_off, d_env_len, max_env_len, W, trig, w2, r0);
         }
         NCFA_LAUNCH_OK("tg_r0_kernel");
     }
