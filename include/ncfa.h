@@ -59,6 +59,14 @@ int ncfa_window_energy(const float *d_audio, const int64_t *d_seg_off, const int
  * n_frames = 1 + n/hop.  float32 like librosa for float32 input. */
 int ncfa_rms_frames(const float *d_audio, int64_t n, int frame_length, int hop, float *d_rms, void *stream);
 
+/* Batched io.strip_silence bounds (io.py:58-79 → librosa.effects.trim(top_db), frame 2048 / hop 512): for every
+ * segment d_bounds[2i] = start, d_bounds[2i+1] = end (samples, relative to the segment; (0, 0) when no frame is
+ * above −top_db relative to the loudest frame).  One pass over the samples (512-sample block sums in float64). */
+size_t ncfa_trim_workspace_bytes(int n_seg, int max_seg_len);
+int ncfa_trim_bounds_batched(const float *d_audio, const int64_t *d_seg_off, const int32_t *d_seg_len, int n_seg,
+                             int max_seg_len, double top_db, int64_t *d_bounds, void *d_workspace,
+                             size_t workspace_bytes, void *stream);
+
 /* ---- tempo.py:44,158  librosa.onset.onset_strength(y, sr, hop_length) -----------------------------
  * For each segment: STFT(2048, hop, periodic Hann, centred, zero pad) → |.|^2 → Slaney mel(128)
  * → 10·log10(max(1e-10,.)) → clamp to (max over the segment − 80 dB) → positive first difference

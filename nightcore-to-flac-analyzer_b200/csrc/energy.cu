@@ -59,6 +59,88 @@ __global__ void __launch_bounds__(256) rms_frames_kernel(const float *__restrict
     if (lane == 0) out[f] = (float)sqrt(acc / (double)frame_length);
 }
 
+
+// ---- batched librosa.effects.trim bounds (io.py:58-79 for every track of a batch, no host round trip per track)
+// Frame f (2048 samples centred on f·512, zero padded) is the union of four 512-sample blocks, so every sample is
+// read once: pass 1 writes float64 block sums, pass 2 forms rms[f] = float32(sqrt(Σ4 blocks / 2048)), the track
+// maximum, db = 10·log10(max(1e-10, rms²)) − 10·log10(max(1e-10, max²)) in float32 like numpy on float32 input, and
+// the first / last frame with db > −top_db → start = 512·first, end = min(n, 512·(last + 1)); none → (0, 0).
+__global__ void __launch_bounds__(256) trim_blocksum_kernel(const float *__restrict__ audio,
+                                                            const int64_t *__restrict__ seg_off,
+                                                            const int32_t *__restrict__ seg_len, int block_stride,
+                                                            double *__restrict__ bsum) {
+    const int seg = blockIdx.y;
+    const int n = seg_len[seg];
+    const int n_blocks = n / 512 + 4;  // blocks j = 0 .. n_frames + 2, block j = samples [(j−2)·512, (j−1)·512)
+    const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (j >= n_blocks) return;
+    const int lane = threadIdx.x & 31;
+    const float *x = audio + seg_off[seg];
+    const int64_t s0 = ((int64_t)j - 2) * 512;
+    double acc = 0.0;
+#pragma unroll 4
+    for (int i = lane; i < 512; i += 32) {
+        const int64_t p = s0 + i;
+        if (p >= 0 && p < n) {
+            const double v = (double)__ldg(x + p);
+            acc = fma(v, v, acc);
+        }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) bsum[(size_t)seg * block_stride + j] = acc;
+}
+
+__global__ void __launch_bounds__(256) trim_bounds_kernel(const int32_t *__restrict__ seg_len, int block_stride,
+                                                          const double *__restrict__ bsum, float top_db,
+                                                          int64_t *__restrict__ bounds) {
+    __shared__ float s_max[256];
+    __shared__ int s_lo[256], s_hi[256];
+    const int seg = blockIdx.x;
+    const int n = seg_len[seg];
+    const int n_frames = 1 + n / 512;
+    const double *b = bsum + (size_t)seg * block_stride;
+    auto rms_of = [&](int f) { return (float)sqrt((((b[f] + b[f + 1]) + b[f + 2]) + b[f + 3]) / 2048.0); };
+    float mx = 0.0f;
+    for (int f = threadIdx.x; f < n_frames; f += 256) mx = fmaxf(mx, rms_of(f));
+    s_max[threadIdx.x] = mx;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) s_max[threadIdx.x] = fmaxf(s_max[threadIdx.x], s_max[threadIdx.x + o]);
+        __syncthreads();
+    }
+    mx = s_max[0];
+    const float ref_db = __fmul_rn(10.0f, log10f(fmaxf(1e-10f, __fmul_rn(mx, mx))));
+    int lo = 0x7fffffff, hi = -1;
+    for (int f = threadIdx.x; f < n_frames; f += 256) {
+        const float m = rms_of(f);
+        const float db = __fsub_rn(__fmul_rn(10.0f, log10f(fmaxf(1e-10f, __fmul_rn(m, m)))), ref_db);
+        if (db > -top_db) {
+            lo = f < lo ? f : lo;
+            hi = f > hi ? f : hi;
+        }
+    }
+    s_lo[threadIdx.x] = lo;
+    s_hi[threadIdx.x] = hi;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            s_lo[threadIdx.x] = min(s_lo[threadIdx.x], s_lo[threadIdx.x + o]);
+            s_hi[threadIdx.x] = max(s_hi[threadIdx.x], s_hi[threadIdx.x + o]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        int64_t start = 0, end = 0;
+        if (s_hi[0] >= 0) {
+            start = (int64_t)s_lo[0] * 512;
+            end = (int64_t)(s_hi[0] + 1) * 512;
+            if (end > n) end = n;
+        }
+        bounds[2 * seg] = start;
+        bounds[2 * seg + 1] = end;
+    }
+}
+
 }  // namespace ncfa
 
 using namespace ncfa;
@@ -87,5 +169,38 @@ extern "C" int ncfa_rms_frames(const float *d_audio, int64_t n, int frame_length
                                                                                        n_frames, d_rms);
     }
     NCFA_LAUNCH_OK("rms_frames_kernel");
+    return NCFA_OK;
+}
+
+extern "C" size_t ncfa_trim_workspace_bytes(int n_seg, int max_seg_len) {
+    if (n_seg <= 0 || max_seg_len < 0) return 0;
+    return align_up((size_t)n_seg * ((size_t)max_seg_len / 512 + 4) * 8, 256);
+}
+
+extern "C" int ncfa_trim_bounds_batched(const float *d_audio, const int64_t *d_seg_off, const int32_t *d_seg_len,
+                                        int n_seg, int max_seg_len, double top_db, int64_t *d_bounds, void *d_workspace,
+                                        size_t workspace_bytes, void *stream) {
+    NCFA_REQUIRE(n_seg >= 0 && n_seg <= 65535, "n_seg must be in [0, 65535] per call");
+    if (n_seg == 0) return NCFA_OK;
+    NCFA_REQUIRE(d_audio && d_seg_off && d_seg_len && d_bounds && d_workspace, "null pointer");
+    NCFA_REQUIRE(max_seg_len >= 0, "max_seg_len");
+    if (workspace_bytes < ncfa_trim_workspace_bytes(n_seg, max_seg_len)) {
+        set_error("trim workspace too small");
+        return NCFA_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int stride = max_seg_len / 512 + 4;
+    double *bsum = (double *)d_workspace;
+    {
+        ProfScope _p("trim_blocksum_kernel", st);
+        dim3 g((stride + 7) / 8, n_seg);
+        trim_blocksum_kernel<<<g, 256, 0, st>>>(d_audio, d_seg_off, d_seg_len, stride, bsum);
+    }
+    NCFA_LAUNCH_OK("trim_blocksum_kernel");
+    {
+        ProfScope _p("trim_bounds_kernel", st);
+        trim_bounds_kernel<<<n_seg, 256, 0, st>>>(d_seg_len, stride, bsum, (float)top_db, d_bounds);
+    }
+    NCFA_LAUNCH_OK("trim_bounds_kernel");
     return NCFA_OK;
 }

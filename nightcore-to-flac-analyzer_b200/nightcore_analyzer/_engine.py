@@ -97,6 +97,25 @@ class Engine:
         self.launches += 1
         return out
 
+    def trim_bounds_dev(self, audio: torch.Tensor, seg_off: np.ndarray, seg_len: np.ndarray, top_db: float) -> torch.Tensor:
+        """librosa.effects.trim bounds of every segment → int64 [n_seg, 2] (start, end) on the device."""
+        n_seg = len(seg_len)
+        out = torch.zeros((max(n_seg, 1), 2), dtype=torch.int64, device=self.device)
+        if n_seg == 0:
+            return out[:0]
+        d_off, d_len = self.to_dev(seg_off.astype(np.int64)), self.to_dev(seg_len.astype(np.int32))
+        with torch.cuda.device(self.device):
+            st = self._stream()
+            for s in range(0, n_seg, MAX_SEGS_PER_CALL):
+                e = min(n_seg, s + MAX_SEGS_PER_CALL)
+                mx = int(seg_len[s:e].max())
+                ws = self.workspace("trim", lib.ncfa_trim_workspace_bytes(e - s, mx))
+                check(lib.ncfa_trim_bounds_batched(_ptr(audio), d_off.data_ptr() + 8 * s, d_len.data_ptr() + 4 * s, e - s, mx,
+                                                   float(top_db), out.data_ptr() + 16 * s, _ptr(ws), ws.numel(), st),
+                      "ncfa_trim_bounds_batched")
+                self.launches += 2
+        return out[:n_seg]
+
     # ------------------------------------------------------------------ onset strength
     @staticmethod
     def env_layout(seg_len: np.ndarray, hop: int) -> Tuple[np.ndarray, np.ndarray, int]:

@@ -38,6 +38,8 @@ _SIGNATURES = {
     "ncfa_profile_report": (c_int, [ctypes.c_char_p, c_size_t]),
     "ncfa_window_energy": (c_int, [_P, _P, _P, c_int, _P, _P]),
     "ncfa_rms_frames": (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
+    "ncfa_trim_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "ncfa_trim_bounds_batched": (c_int, [_P, _P, _P, c_int, c_int, c_double, _P, _P, c_size_t, _P]),
     "ncfa_onset_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "ncfa_onset_strength_batched": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P]),
     "ncfa_tempo_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),

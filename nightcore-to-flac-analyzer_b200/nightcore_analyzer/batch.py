@@ -113,22 +113,9 @@ def analyse_staged(batch: StagedBatch, *, window_sec: float = WINDOW_SEC, hop_se
 
     # ---- stage 1: strip_silence (io.py:58-79) — bounds only; the samples never move
     if silence_strip_db is not None and n_tracks:
-        rms_list = [eng.rms_frames_dev(batch.audio[int(o):], int(n), 2048, 512) if n > 0 else None
-                    for o, n in zip(t_off, t_len)]
-        amin = 1e-5
-        for k, r in enumerate(rms_list):
-            if r is None:
-                continue
-            mag = np.abs(eng.to_host(r))
-            ref = np.max(mag)
-            db = 10.0 * np.log10(np.maximum(amin ** 2, mag ** 2)) - 10.0 * np.log10(np.maximum(amin ** 2, ref ** 2))
-            ns = np.flatnonzero(db > -silence_strip_db)
-            if ns.size:
-                s, e = int(ns[0] * 512), min(int(t_len[k]), int((ns[-1] + 1) * 512))
-            else:
-                s, e = 0, 0
-            t_off[k] += s
-            t_len[k] = e - s
+        bounds = eng.to_host(eng.trim_bounds_dev(batch.audio, t_off, t_len.astype(np.int32), silence_strip_db))
+        t_off = t_off + bounds[:, 0]
+        t_len = bounds[:, 1] - bounds[:, 0]
 
     # ---- stage 2: windows, float64 energies, gate (io.py:82-126)
     win_n, hop_n = int(window_sec * sr), int(hop_sec * sr)
@@ -142,7 +129,7 @@ def analyse_staged(batch: StagedBatch, *, window_sec: float = WINDOW_SEC, hop_se
     seg_len = np.full(len(seg_off), win_n, dtype=np.int32)
     if len(seg_off):
         ms = eng.window_energy_dev(batch.audio, eng.to_dev(seg_off), eng.to_dev(seg_len)).cpu().numpy()
-        energy_db = np.array([_db_from_meansq(float(m)) for m in ms])
+        energy_db = 20.0 * np.log10(np.maximum(np.sqrt(ms), 1e-10))        # io.py:38-40, vectorised
     else:
         energy_db = np.zeros(0)
     cnt = np.bincount(seg_track, minlength=n_tracks) if len(seg_track) else np.zeros(n_tracks, np.int64)
@@ -185,9 +172,24 @@ def analyse_staged(batch: StagedBatch, *, window_sec: float = WINDOW_SEC, hop_se
     pair_of = seg_track // 2
     sel_src = np.flatnonzero(keep & is_src & alive[pair_of])
     lag_s, nb_s = run_tempo(sel_src, np.full(len(sel_src), 120.0))
-    src_tempos: List[list] = [[] for _ in range(P)]
-    for j, s in enumerate(sel_src):
-        src_tempos[pair_of[s]].append(_tempo._consensus(int(lag_s[j]), int(nb_s[j]), sr, _tempo.HOP_LENGTH))
+    def per_pair_tempos(sel, lag, nb):
+        """tempo.py:51-77 for every window at once: both estimators equal bpms[lag] ⇒ that value when the window has
+        >= MIN_BEATS beats and a positive lag, else None; split into one list per pair (window order preserved)."""
+        out: List[list] = [[] for _ in range(P)]
+        if len(sel) == 0:
+            return out
+        ok = (nb >= _tempo.MIN_BEATS) & (lag > 0)
+        bpm = 60.0 * sr / (_tempo.HOP_LENGTH * np.where(ok, lag, 1).astype(np.float64))
+        vals = [float(b) if o else None for b, o in zip(bpm.tolist(), ok.tolist())]
+        owners = pair_of[sel]
+        cuts = np.flatnonzero(np.diff(owners)) + 1
+        starts = np.concatenate([[0], cuts])
+        ends = np.concatenate([cuts, [len(sel)]])
+        for a, b in zip(starts, ends):
+            out[int(owners[a])] = vals[a:b]
+        return out
+
+    src_tempos = per_pair_tempos(sel_src, lag_s, nb_s)
 
     # ---- stage 5: per-pair prior (pipeline.py:171-178)
     nc_dur = t_len[0::2] / sr
@@ -201,9 +203,7 @@ def analyse_staged(batch: StagedBatch, *, window_sec: float = WINDOW_SEC, hop_se
     # ---- stage 6: nightcore windows with the pair's prior
     sel_nc = np.flatnonzero(keep & ~is_src & alive[pair_of])
     lag_n, nb_n = run_tempo(sel_nc, prior[pair_of[sel_nc]] if len(sel_nc) else np.zeros(0))
-    nc_tempos: List[list] = [[] for _ in range(P)]
-    for j, s in enumerate(sel_nc):
-        nc_tempos[pair_of[s]].append(_tempo._consensus(int(lag_n[j]), int(nb_n[j]), sr, _tempo.HOP_LENGTH))
+    nc_tempos = per_pair_tempos(sel_nc, lag_n, nb_n)
 
     # ---- stage 7: hop-64 whole-track pass (tempo.py:120-173) for every live pair
     ibis: List[Optional[Tuple[np.ndarray, np.ndarray]]] = [None] * P
@@ -281,3 +281,48 @@ def analyse_staged(batch: StagedBatch, *, window_sec: float = WINDOW_SEC, hop_se
 def run_batch_arrays(pairs: Sequence[Tuple[np.ndarray, np.ndarray]], sr: int = SAMPLE_RATE, **kwargs):
     """[(nc_audio, src_audio), ...] → [AnalysisResult | Exception, ...] (same kwargs as analyse_staged)."""
     return analyse_staged(stage_pairs(pairs, sr), **kwargs)
+
+
+def analyse_pinned(pb: PinnedBatch, sizes: Sequence[int], stats: Optional[dict] = None, **kwargs):
+    """End-to-end form of the batch scheduler: the pairs of a pinned host batch are analysed in sub-batches of
+    ``sizes`` pairs each (every sub-batch reads the first ``k`` pairs of ``pb`` — bench.py tiles one composition), and
+    the pinned→HBM copy of sub-batch i+1 runs on a second stream while sub-batch i is analysed."""
+    eng = _engine.get_engine()
+    copy_stream = _copy_stream(eng.device)
+    main = torch.cuda.current_stream(eng.device)
+    results: list = []
+    total_h2d = 0
+
+    def start_upload(k):
+        copy_stream.wait_stream(main)          # the buffer the allocator hands out may have been used on `main`
+        with torch.cuda.stream(copy_stream):
+            st = upload(pb, k)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return st, ev
+
+    nxt = start_upload(sizes[0]) if sizes else None
+    for i, k in enumerate(sizes):
+        cur, ev = nxt
+        main.wait_event(ev)
+        cur.audio.record_stream(main)
+        nxt = start_upload(sizes[i + 1]) if i + 1 < len(sizes) else None
+        s1: dict = {}
+        results += analyse_staged(cur, stats=s1, **kwargs)
+        total_h2d += cur.h2d_bytes
+        if stats is not None:
+            for key, v in s1.items():
+                stats[key] = stats.get(key, 0) + v
+    if stats is not None:
+        stats["h2d_bytes"] = total_h2d
+    return results
+
+
+_COPY_STREAMS: dict = {}
+
+
+def _copy_stream(device) -> "torch.cuda.Stream":
+    key = torch.device(device).index
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _COPY_STREAMS[key]

@@ -105,17 +105,8 @@ def strip_silence(audio: np.ndarray, sr: int, top_db: float = SILENCE_STRIP_DB) 
     n = len(a)
     if n == 0:
         return audio[0:0], 0.0, 0.0
-    rms = eng.rms_frames_dev(eng.to_dev(a), n, 2048, 512).cpu().numpy()
-    amin = 1e-5
-    mag = np.abs(rms)
-    ref = np.max(mag)
-    db = 10.0 * np.log10(np.maximum(amin ** 2, mag ** 2)) - 10.0 * np.log10(np.maximum(amin ** 2, ref ** 2))
-    non_silent = np.flatnonzero(db > -top_db)
-    if non_silent.size > 0:
-        start = int(non_silent[0] * 512)
-        end = min(n, int((non_silent[-1] + 1) * 512))
-    else:
-        start, end = 0, 0
+    bounds = eng.to_host(eng.trim_bounds_dev(eng.to_dev(a), np.zeros(1, np.int64), np.array([n], np.int32), top_db))
+    start, end = int(bounds[0, 0]), int(bounds[0, 1])
     trimmed = audio[start:end]
     return trimmed, start / sr, (len(audio) - end) / sr
 
