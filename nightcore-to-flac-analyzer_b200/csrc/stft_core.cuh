@@ -40,7 +40,9 @@ __device__ __forceinline__ cf mul_w64(cf a) {
 
 template <int K2>
 struct PostStage {
-    // un-pack bin k = lane + 32·K2 of the real FFT and store its power
+    // Un-pack the real FFT from the packed complex one and store powers.  With E = ½(Z[k] + conj Z[N−k]),
+    // O = (Z[k] − conj Z[N−k])/(2i), W = W_2048^k:  X[k] = E + W·O and X[1024−k] = conj(E − W·O), so one (E, W·O)
+    // pair yields both bins: K2 runs over 0..15 only (k = lane + 32·K2 < 512), bin 512 is |Z[512]|².
     static __device__ __forceinline__ void run(const cf (&v)[32], int lane, cf twl, float *pw) {
         cf zk = v[br5(K2)];
         cf own = v[br5((32 - K2) & 31)];
@@ -55,12 +57,16 @@ struct PostStage {
         cf w = mul_w64<K2>(twl);  // W_2048^(lane + 32·K2)
         cf wo = cmul(w, o);
         cf x = cadd(e, wo);
+        cf y = csub(e, wo);
         pw[lane + 32 * K2] = x.x * x.x + x.y * x.y;
-        if (K2 == 0 && lane == 0) {
-            float ny = e.x - o.x;  // bin 1024
-            pw[1024] = ny * ny;
+        pw[1024 - lane - 32 * K2] = y.x * y.x + y.y * y.y;
+        if constexpr (K2 + 1 < 16) PostStage<K2 + 1>::run(v, lane, twl, pw);
+        if constexpr (K2 == 0) {
+            if (lane == 0) {
+                cf z = v[br5(16)];
+                pw[512] = z.x * z.x + z.y * z.y;
+            }
         }
-        if constexpr (K2 + 1 < 32) PostStage<K2 + 1>::run(v, lane, twl, pw);
     }
 };
 
