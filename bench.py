@@ -95,11 +95,20 @@ class ClockSampler:
 
 # --------------------------------------------------------------------------------------- CPU arm
 def _cpu_one_pair(args):
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    """One pair through the CPU port in a worker process.  BLAS/OpenMP pools are pinned to one thread so that P
+    processes use P cores (without this the einsum/BLAS pools oversubscribe the box and the baseline is ~3x slower)."""
     nc, src = args
     from oracle import pipeline_port
+    try:
+        from threadpoolctl import threadpool_limits
+    except Exception:  # pragma: no cover
+        threadpool_limits = None
     t0 = time.perf_counter()
-    res, n_windows = pipeline_port.run_arrays(nc, src, SR, log=None, return_window_count=True)
+    if threadpool_limits is not None:
+        with threadpool_limits(limits=1):
+            res, n_windows = pipeline_port.run_arrays(nc, src, SR, log=None, return_window_count=True)
+    else:
+        res, n_windows = pipeline_port.run_arrays(nc, src, SR, log=None, return_window_count=True)
     return n_windows, time.perf_counter() - t0
 
 
