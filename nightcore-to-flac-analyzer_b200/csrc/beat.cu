@@ -157,24 +157,38 @@ __global__ void beat_track_kernel(const float *__restrict__ onset, const int64_t
         first = block_reduce(first, sh_i, [](int a, int b) { return a < b ? a : b; });
     }
 
-    // ---- DP over wavefronts of `near` frames
+    // ---- DP over wavefronts of `near` frames; inside a wavefront one WARP owns a frame and its lanes share the
+    // scan over the predecessors loc = i−near … i−2·fpb (nearest first).  librosa keeps the first strict maximum in
+    // that order; the lane-local strict > plus the (score, larger loc) reduction reproduces it exactly.
+    const int lane_ = tid & 31, warp_ = tid >> 5, nwarps = nt >> 5;
     for (int basei = 0; basei < N; basei += near) {
-        for (int j = tid; j < near; j += nt) {
+        for (int j = warp_; j < near; j += nwarps) {
             const int i = basei + j;
             if (i < N) {
                 double best = -INFINITY;
                 int bl = -1;
                 int lo = i - far;
                 if (lo < 0) lo = 0;
-                for (int loc = i - near; loc >= lo; --loc) {
-                    double sc = cum[loc] - pen[i - loc - near];
+                for (int loc = i - near - lane_; loc >= lo; loc -= 32) {
+                    const double sc = cum[loc] - pen[i - loc - near];
                     if (sc > best) {
                         best = sc;
                         bl = loc;
                     }
                 }
-                cum[i] = (bl >= 0) ? ls[i] + best : ls[i];
-                backlink[i] = (i < first) ? -1 : bl;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+                    if (ol >= 0 && (bl < 0 || ob > best || (ob == best && ol > bl))) {
+                        best = ob;
+                        bl = ol;
+                    }
+                }
+                if (lane_ == 0) {
+                    cum[i] = (bl >= 0) ? ls[i] + best : ls[i];
+                    backlink[i] = (i < first) ? -1 : bl;
+                }
             }
         }
         __syncthreads();
