@@ -157,38 +157,43 @@ __global__ void beat_track_kernel(const float *__restrict__ onset, const int64_t
         first = block_reduce(first, sh_i, [](int a, int b) { return a < b ? a : b; });
     }
 
-    // ---- DP over wavefronts of `near` frames; inside a wavefront one WARP owns a frame and its lanes share the
-    // scan over the predecessors loc = i−near … i−2·fpb (nearest first).  librosa keeps the first strict maximum in
-    // that order; the lane-local strict > plus the (score, larger loc) reduction reproduces it exactly.
-    const int lane_ = tid & 31, warp_ = tid >> 5, nwarps = nt >> 5;
+    // ---- DP over wavefronts of `near` independent frames.  A frame is owned by a group of L lanes (L = largest power
+    // of two with near·L <= blockDim, at most 32) that share the scan over the predecessors loc = i−near … i−2·fpb
+    // (nearest first).  librosa keeps the first strict maximum in that order; the lane-local strict > plus the
+    // (score, larger loc) reduction reproduces it exactly.
+    int L = 1;
+    while (L < 32 && near * (2 * L) <= nt) L *= 2;
+    const int ngroups = nt / L, grp = tid / L, sub = tid % L;
+    const int rounds = (near + ngroups - 1) / ngroups;
     for (int basei = 0; basei < N; basei += near) {
-        for (int j = warp_; j < near; j += nwarps) {
+        for (int r = 0; r < rounds; ++r) {  // warp-uniform trip count: every lane takes part in the shuffles
+            const int j = r * ngroups + grp;
             const int i = basei + j;
-            if (i < N) {
-                double best = -INFINITY;
-                int bl = -1;
+            const bool active = j < near && i < N;
+            double best = -INFINITY;
+            int bl = -1;
+            if (active) {
                 int lo = i - far;
                 if (lo < 0) lo = 0;
-                for (int loc = i - near - lane_; loc >= lo; loc -= 32) {
+                for (int loc = i - near - sub; loc >= lo; loc -= L) {
                     const double sc = cum[loc] - pen[i - loc - near];
                     if (sc > best) {
                         best = sc;
                         bl = loc;
                     }
                 }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-                    const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
-                    if (ol >= 0 && (bl < 0 || ob > best || (ob == best && ol > bl))) {
-                        best = ob;
-                        bl = ol;
-                    }
+            }
+            for (int o = L >> 1; o > 0; o >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+                if (ol >= 0 && (bl < 0 || ob > best || (ob == best && ol > bl))) {
+                    best = ob;
+                    bl = ol;
                 }
-                if (lane_ == 0) {
-                    cum[i] = (bl >= 0) ? ls[i] + best : ls[i];
-                    backlink[i] = (i < first) ? -1 : bl;
-                }
+            }
+            if (active && sub == 0) {
+                cum[i] = (bl >= 0) ? ls[i] + best : ls[i];
+                backlink[i] = (i < first) ? -1 : bl;
             }
         }
         __syncthreads();
@@ -293,7 +298,7 @@ extern "C" int ncfa_beat_track_batched(const float *d_onset, const int64_t *d_on
     double *wf = (double *)d_workspace;
     int32_t *wi = (int32_t *)((char *)d_workspace +
                               align_up((size_t)n_seg * beat_f64_per_seg(max_env_len, max_lag) * 8, 256));
-    const int threads = max_env_len <= 2048 ? 64 : 256;
+    const int threads = max_env_len <= 2048 ? 64 : 512;
     {
         ProfScope _p("beat_track_kernel", (cudaStream_t)stream);
         beat_track_kernel<<<n_seg, threads, threads * sizeof(double), (cudaStream_t)stream>>>(
