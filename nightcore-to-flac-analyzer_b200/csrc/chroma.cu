@@ -684,8 +684,11 @@ constexpr int kTcACols = 2 * kTcKT;                      // hi + lo columns of o
 constexpr int kTcAccCol0 = kTcAStages * kTcACols;        // 256
 constexpr int kTcTmemCols = 512;                         // 256 (A ring) + 2 × 80 (accumulators) → next power of two
 
+constexpr int kTcAPre = 4;  // k-tiles of A rows in flight per frame thread (cp.async ring in shared memory)
+
 struct TcSmem {
     alignas(1024) unsigned char b[kTcBStages][kTcBStageBytes];
+    float4 arow[kTcAPre][8][kTcFrames];  // [slot][16-byte chunk][frame]: conflict-free for cp.async and LDS.128
     alignas(8) uint64_t full_a[kTcAStages], empty_a[kTcAStages], full_b[kTcBStages], empty_b[kTcBStages];
     uint64_t acc_full[2], acc_empty[2];
     uint32_t tmem_base;
@@ -793,43 +796,76 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
             }
         };
 
-        for (int o = 0; o < kOctaves; ++o) {
+        // A rows stream through a per-thread cp.async ring (kTcAPre k-tiles ahead, flat over octaves × k-tiles) so the
+        // global-load latency never sits in front of the tcgen05.st; zero padding outside [0, len) comes from the
+        // src-size (zfill) form — row starts are multiples of 4 samples, so a 16-byte chunk never straddles 0.
+        const float *y0 = audio + seg_off[seg];
+        const bool y0_aligned = (reinterpret_cast<uintptr_t>(y0) & 15u) == 0;
+        auto issue = [&](int it) {
+            const int o = it >> 5, kt = it & 31;
             const int hop = 512 >> o;
-            const float *y = (o == 0) ? audio + seg_off[seg] : pseg + po.off[o];
+            const float *y = (o == 0) ? y0 : pseg + po.off[o];
             const int len = level_len(n, o);
-            const int64_t row0 = (int64_t)(t0 + f) * hop - kCqtNfft / 2;
-            float x[32];
-            tc_load_row32(y, row0, len, x);
-            for (int kt = 0; kt < kKTiles; ++kt) {
-                const int it = o * kKTiles + kt;
-                const int st = it % kTcAStages;
-                float xn[32];
-                if (kt + 1 < kKTiles) tc_load_row32(y, row0 + (int64_t)(kt + 1) * kTcKT, len, xn);  // prefetch
-                mbar_wait(&sm.empty_a[st], (uint32_t)(((it / kTcAStages) & 1) ^ 1));
-                fence_after_sync();
-                const uint32_t a0 = tmem + lane_base + (uint32_t)(st * kTcACols);
-                uint32_t h[16], l[16];
+            const int64_t base = (int64_t)(t0 + f) * hop - kCqtNfft / 2 + (int64_t)kt * kTcKT;
+            float4 *slot = &sm.arow[it % kTcAPre][0][f];
+            if (o > 0 || y0_aligned) {
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float xv = x[16 * half + i];
-                        const float hi = to_tf32(xv);
-                        h[i] = __float_as_uint(hi);
-                        l[i] = __float_as_uint(xv - hi);
-                    }
-                    tmem_st16(a0 + 16 * half, h);
-                    tmem_st16(a0 + kTcKT + 16 * half, l);
+                for (int c = 0; c < 8; ++c) {
+                    const int64_t pos = base + 4 * c;
+                    int64_t rem = ((int64_t)len - pos) * 4;
+                    const uint32_t bytes = pos < 0 ? 0u : (uint32_t)(rem < 0 ? 0 : (rem > 16 ? 16 : rem));
+                    const float *src = bytes ? y + pos : y;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(slot + c * kTcFrames)),
+                                 "l"(src), "r"(bytes)
+                                 : "memory");
                 }
-                wait_st();
-                fence_before_sync();
-                mbar_arrive(&sm.full_a[st]);
-                if (kt + 1 < kKTiles) {
+            } else {  // unaligned first level (arbitrary caller offset): plain loads into the same slot
+                float xr[32];
+                tc_load_row32(y, base, len, xr);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) x[i] = xn[i];
+                for (int c = 0; c < 8; ++c) slot[c * kTcFrames] = make_float4(xr[4 * c], xr[4 * c + 1], xr[4 * c + 2], xr[4 * c + 3]);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        for (int it = 0; it < kTcAPre - 1; ++it) issue(it);
+        for (int it = 0; it < kIters; ++it) {
+            if (it + kTcAPre - 1 < kIters) issue(it + kTcAPre - 1);
+            else asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group %0;" ::"n"(kTcAPre - 1) : "memory");
+            const int o = it >> 5, kt = it & 31;
+            const int st = it % kTcAStages;
+            float x[32];
+            {
+                const float4 *slot = &sm.arow[it % kTcAPre][0][f];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 v = slot[c * kTcFrames];
+                    x[4 * c] = v.x;
+                    x[4 * c + 1] = v.y;
+                    x[4 * c + 2] = v.z;
+                    x[4 * c + 3] = v.w;
                 }
             }
-            if (o > 0) epilogue(o - 1);
+            mbar_wait(&sm.empty_a[st], (uint32_t)(((it / kTcAStages) & 1) ^ 1));
+            fence_after_sync();
+            const uint32_t a0 = tmem + lane_base + (uint32_t)(st * kTcACols);
+            uint32_t h[16], l[16];
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float xv = x[16 * half + i];
+                    const float hi = to_tf32(xv);
+                    h[i] = __float_as_uint(hi);
+                    l[i] = __float_as_uint(xv - hi);
+                }
+                tmem_st16(a0 + 16 * half, h);
+                tmem_st16(a0 + kTcKT + 16 * half, l);
+            }
+            wait_st();
+            fence_before_sync();
+            mbar_arrive(&sm.full_a[st]);
+            if (kt == kKTiles - 1 && o > 0) epilogue(o - 1);
         }
         epilogue(kOctaves - 1);
 
