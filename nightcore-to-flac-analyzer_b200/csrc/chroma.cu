@@ -665,7 +665,11 @@ __global__ void __launch_bounds__(kCqtThreads) cqt_chroma_kernel(const float *__
 
 // ------------------------------------------------------------------------------------------------ CQT on tcgen05
 // Same contraction on the 5th-generation tensor cores:  D[128 frames × 80] (+)= A[128 × 8]·B[80 × 8]^T, kind::tf32,
-// with the 3×TF32 split  x = hi + lo  (hi = rna_tf32(x), lo = x − hi exactly):  A·B ≈ Ah·Bh + Al·Bh + Ah·Bl.
+// with the TF32 split  x = hi + lo  (hi = rna_tf32(x), lo = x − hi exactly).  The hi and lo images of B are stacked
+// along N (one 160-row K-major tile [Bh; Bl]), so ONE MMA with N = 160 yields A·Bh in columns 0..79 and A·Bl in
+// columns 80..159; issuing it for A = Ah and A = Al accumulates all four partial products with 2 instructions per
+// K = 8 step (small-N tf32 MMAs are issue bound: 3 × N=80 instructions per step ran the tensor pipe at 25 %), and
+// the epilogue adds the two column halves.
 //   A (the Hankel matrix of frames) is never materialised in memory: frame thread f keeps row f, reads its 32 samples of
 //     the k-tile straight from global memory (L1/L2 serve the overlap between frames), splits them in registers and
 //     writes hi / lo into TENSOR MEMORY with tcgen05.st; the MMA reads A from TMEM (TS form).
@@ -678,11 +682,12 @@ __global__ void __launch_bounds__(kCqtThreads) cqt_chroma_kernel(const float *__
 // shared memory), accumulator ring (2).
 constexpr int kTcFrames = 128;
 constexpr int kTcThreads = 192;
-constexpr int kTcAStages = 4;
+constexpr int kTcAStages = 3;
 constexpr int kTcBStages = 6;
 constexpr int kTcACols = 2 * kTcKT;                      // hi + lo columns of one A stage
-constexpr int kTcAccCol0 = kTcAStages * kTcACols;        // 256
-constexpr int kTcTmemCols = 512;                         // 256 (A ring) + 2 × 80 (accumulators) → next power of two
+constexpr int kTcAccCol0 = kTcAStages * kTcACols;        // 192
+constexpr int kTcAccN = 2 * kTcN;                        // accumulator columns: [A·Bh | A·Bl]
+constexpr int kTcTmemCols = 512;                         // 192 (A ring) + 2 × 160 (accumulators)
 
 constexpr int kTcAPre = 4;  // k-tiles of A rows in flight per frame thread (cp.async ring in shared memory)
 
@@ -771,20 +776,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
             const int buf = o & 1;
             mbar_wait(&sm.acc_full[buf], (uint32_t)((o >> 1) & 1));
             fence_after_sync();
-            float re[kCqtBins];
-            // columns 0..35 real parts, 36..71 imaginary parts
-            uint32_t v[16];
-            const uint32_t acc = tmem + lane_base + (uint32_t)(kTcAccCol0 + buf * kTcN);
-            float im[kCqtBins];
+            // columns 0..35 / 36..71: real / imaginary parts of A·Bh; 80..115 / 116..151: the same for A·Bl
+            float re[kCqtBins], im[kCqtBins];
 #pragma unroll
-            for (int g = 0; g < 5; ++g) {
+            for (int b = 0; b < kCqtBins; ++b) re[b] = im[b] = 0.0f;
+            uint32_t v[16];
+            const uint32_t acc = tmem + lane_base + (uint32_t)(kTcAccCol0 + buf * kTcAccN);
+#pragma unroll
+            for (int g = 0; g < kTcAccN / 16; ++g) {
                 tmem_ld16(acc + 16 * g, v);
                 wait_ld();
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const int col = 16 * g + i;
-                    if (col < kCqtBins) re[col] = __uint_as_float(v[i]);
-                    else if (col < 2 * kCqtBins) im[col - kCqtBins] = __uint_as_float(v[i]);
+                    const int col = (16 * g + i) % kTcN;
+                    if (col < kCqtBins) re[col] += __uint_as_float(v[i]);
+                    else if (col < 2 * kCqtBins) im[col - kCqtBins] += __uint_as_float(v[i]);
                 }
             }
             fence_before_sync();
@@ -888,27 +894,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
     } else if (warp == 4) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = idesc_tf32(kTcFrames, kTcN);
+            constexpr uint32_t idesc = idesc_tf32(kTcFrames, kTcAccN);
             for (int o = 0; o < kOctaves; ++o) {
                 const int buf = o & 1;
                 mbar_wait(&sm.acc_empty[buf], (uint32_t)(((o >> 1) & 1) ^ 1));
                 fence_after_sync();
-                const uint32_t d = tmem + (uint32_t)(kTcAccCol0 + buf * kTcN);
+                const uint32_t d = tmem + (uint32_t)(kTcAccCol0 + buf * kTcAccN);
                 for (int kt = 0; kt < kKTiles; ++kt) {
                     const int it = o * kKTiles + kt;
                     const int sa = it % kTcAStages, sb = it % kTcBStages;
                     mbar_wait(&sm.full_a[sa], (uint32_t)((it / kTcAStages) & 1));
                     mbar_wait(&sm.full_b[sb], (uint32_t)((it / kTcBStages) & 1));
                     fence_after_sync();
-                    const uint64_t bh = smem_desc_k128(sm.b[sb]);
-                    const uint64_t bl = smem_desc_k128(sm.b[sb] + kTcBTileBytes);
+                    const uint64_t bd = smem_desc_k128(sm.b[sb]);  // 160 rows: Bh image then Bl image
                     const uint32_t ah = tmem + (uint32_t)(sa * kTcACols), al = ah + kTcKT;
 #pragma unroll
                     for (int k = 0; k < kTcKT / 8; ++k) {
                         const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 32 bytes per K = 8 step inside the swizzle row
-                        mma_tf32_ts(d, ah + 8 * k, bh + adv, idesc, (kt | k) != 0);
-                        mma_tf32_ts(d, al + 8 * k, bh + adv, idesc, 1);
-                        mma_tf32_ts(d, ah + 8 * k, bl + adv, idesc, 1);
+                        mma_tf32_ts(d, ah + 8 * k, bd + adv, idesc, (kt | k) != 0);
+                        mma_tf32_ts(d, al + 8 * k, bd + adv, idesc, 1);
                     }
                     commit(&sm.empty_a[sa]);
                     commit(&sm.empty_b[sb]);
