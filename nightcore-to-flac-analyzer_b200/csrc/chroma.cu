@@ -892,22 +892,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
             partial[((size_t)seg * tile_stride + blockIdx.x) * kChroma + tid] =
                 ((sm.red[0][tid] + sm.red[1][tid]) + sm.red[2][tid]) + sm.red[3][tid];
     } else if (warp == 4) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = idesc_tf32(kTcFrames, kTcAccN);
-            for (int o = 0; o < kOctaves; ++o) {
-                const int buf = o & 1;
-                mbar_wait(&sm.acc_empty[buf], (uint32_t)(((o >> 1) & 1) ^ 1));
+        // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
+        constexpr uint32_t idesc = idesc_tf32(kTcFrames, kTcAccN);
+        for (int o = 0; o < kOctaves; ++o) {
+            const int buf = o & 1;
+            mbar_wait(&sm.acc_empty[buf], (uint32_t)(((o >> 1) & 1) ^ 1));
+            fence_after_sync();
+            const uint32_t d = tmem + (uint32_t)(kTcAccCol0 + buf * kTcAccN);
+            for (int kt = 0; kt < kKTiles; ++kt) {
+                const int it = o * kKTiles + kt;
+                const int sa = it % kTcAStages, sb = it % kTcBStages;
+                mbar_wait(&sm.full_a[sa], (uint32_t)((it / kTcAStages) & 1));
+                mbar_wait(&sm.full_b[sb], (uint32_t)((it / kTcBStages) & 1));
                 fence_after_sync();
-                const uint32_t d = tmem + (uint32_t)(kTcAccCol0 + buf * kTcAccN);
-                for (int kt = 0; kt < kKTiles; ++kt) {
-                    const int it = o * kKTiles + kt;
-                    const int sa = it % kTcAStages, sb = it % kTcBStages;
-                    mbar_wait(&sm.full_a[sa], (uint32_t)((it / kTcAStages) & 1));
-                    mbar_wait(&sm.full_b[sb], (uint32_t)((it / kTcBStages) & 1));
-                    fence_after_sync();
-                    const uint64_t bd = smem_desc_k128(sm.b[sb]);  // 160 rows: Bh image then Bl image
-                    const uint32_t ah = tmem + (uint32_t)(sa * kTcACols), al = ah + kTcKT;
+                const uint64_t bd = smem_desc_k128(sm.b[sb]);  // 160 rows: Bh image then Bl image
+                const uint32_t ah = tmem + (uint32_t)(sa * kTcACols), al = ah + kTcKT;
+                if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < kTcKT / 8; ++k) {
                         const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 32 bytes per K = 8 step inside the swizzle row
@@ -916,23 +916,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
                     }
                     commit(&sm.empty_a[sa]);
                     commit(&sm.empty_b[sb]);
+                    if (kt == kKTiles - 1) commit(&sm.acc_full[buf]);
                 }
-                commit(&sm.acc_full[buf]);
+                __syncwarp();
             }
         }
-        __syncwarp();
     } else {
-        // ===================== B loader =====================
-        if (lane == 0) {
-            const unsigned char *src = reinterpret_cast<const unsigned char *>(Bimg) + (size_t)tj * kKTiles * kTcBStageBytes;
-            for (int it = 0; it < kIters; ++it) {
-                const int sb = it % kTcBStages, kt = it % kKTiles;
-                mbar_wait(&sm.empty_b[sb], (uint32_t)(((it / kTcBStages) & 1) ^ 1));
+        // ===================== B loader (warp-uniform, one elected lane issues the bulk copy) =====================
+        const unsigned char *src = reinterpret_cast<const unsigned char *>(Bimg) + (size_t)tj * kKTiles * kTcBStageBytes;
+        for (int it = 0; it < kIters; ++it) {
+            const int sb = it % kTcBStages, kt = it % kKTiles;
+            mbar_wait(&sm.empty_b[sb], (uint32_t)(((it / kTcBStages) & 1) ^ 1));
+            if (elect_one()) {
                 mbar_arrive_expect_tx(&sm.full_b[sb], kTcBStageBytes);
                 bulk_g2s(sm.b[sb], src + (size_t)kt * kTcBStageBytes, kTcBStageBytes, &sm.full_b[sb]);
             }
+            __syncwarp();
         }
-        __syncwarp();
     }
     fence_before_sync();
     __syncthreads();
