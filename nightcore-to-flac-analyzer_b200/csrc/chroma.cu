@@ -739,7 +739,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
 
     if (tid == 0) {
         for (int i = 0; i < kTcAStages; ++i) {
-            mbar_init(&sm.full_a[i], kTcFrames);
+            mbar_init(&sm.full_a[i], 4);  // one arrival per frame warp
             mbar_init(&sm.empty_a[i], 1);
         }
         for (int i = 0; i < kTcBStages; ++i) {
@@ -748,7 +748,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&sm.acc_full[i], 1);
-            mbar_init(&sm.acc_empty[i], kTcFrames);
+            mbar_init(&sm.acc_empty[i], 4);
         }
         fence_mbar_init();
     }
@@ -794,7 +794,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
                 }
             }
             fence_before_sync();
-            mbar_arrive(&sm.acc_empty[buf]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.acc_empty[buf]);
 #pragma unroll
             for (int b = 0; b < kCqtBins; ++b) {
                 const float m = sqrtf(re[b] * re[b] + im[b] * im[b]);
@@ -870,7 +871,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
             }
             wait_st();
             fence_before_sync();
-            mbar_arrive(&sm.full_a[st]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.full_a[st]);  // 128 per-thread arrivals would serialise on one shared word
             if (kt == kKTiles - 1 && o > 0) epilogue(o - 1);
         }
         epilogue(kOctaves - 1);
