@@ -835,6 +835,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
         for (int it = 0; it < kTcAPre - 1; ++it) issue(it);
+        bool pending = false;
         for (int it = 0; it < kIters; ++it) {
             if (it + kTcAPre - 1 < kIters) issue(it + kTcAPre - 1);
             else asm volatile("cp.async.commit_group;" ::: "memory");
@@ -853,27 +854,43 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
                     x[4 * c + 3] = v.w;
                 }
             }
+            // split first (pure ALU), so that this work overlaps the landing of the previous tile's tcgen05.st
+            uint32_t h[32], l[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float hi = to_tf32(x[i]);
+                h[i] = __float_as_uint(hi);
+                l[i] = __float_as_uint(x[i] - hi);
+            }
+            if (pending) {  // publish the PREVIOUS tile: one mbarrier arrival per warp
+                wait_st();
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.full_a[(it - 1) % kTcAStages]);
+            }
             mbar_wait(&sm.empty_a[st], (uint32_t)(((it / kTcAStages) & 1) ^ 1));
             fence_after_sync();
             const uint32_t a0 = tmem + lane_base + (uint32_t)(st * kTcACols);
-            uint32_t h[16], l[16];
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
+                uint32_t hv[16], lv[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const float xv = x[16 * half + i];
-                    const float hi = to_tf32(xv);
-                    h[i] = __float_as_uint(hi);
-                    l[i] = __float_as_uint(xv - hi);
+                    hv[i] = h[16 * half + i];
+                    lv[i] = l[16 * half + i];
                 }
-                tmem_st16(a0 + 16 * half, h);
-                tmem_st16(a0 + kTcKT + 16 * half, l);
+                tmem_st16(a0 + 16 * half, hv);
+                tmem_st16(a0 + kTcKT + 16 * half, lv);
             }
-            wait_st();
-            fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.full_a[st]);  // 128 per-thread arrivals would serialise on one shared word
-            if (kt == kKTiles - 1 && o > 0) epilogue(o - 1);
+            pending = true;
+            if (kt == kKTiles - 1) {  // octave boundary (and the very last tile): publish before the epilogue
+                wait_st();
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.full_a[st]);
+                pending = false;
+                if (o > 0) epilogue(o - 1);
+            }
         }
         epilogue(kOctaves - 1);
 
