@@ -677,46 +677,68 @@ __global__ void __launch_bounds__(kCqtThreads) cqt_chroma_kernel(const float *__
 //     20 KB 1-D bulk async copy (cp.async.bulk + mbarrier complete_tx) — no tensor map needed.
 //   D lives in TMEM, double buffered across octaves; the epilogue (tcgen05.ld → |re + i·im| → fold to 12 chroma) of
 //     octave o−1 overlaps the MMAs of octave o.
-// Warp roles (192 threads): warps 0-3 frame warps (A producer + epilogue, TMEM lanes 32w..32w+31), warp 4 MMA issuer
-// (one lane) and TMEM allocator, warp 5 B loader (one lane).  Pipelines: A ring (4 stages in TMEM), B ring (6 stages in
-// shared memory), accumulator ring (2).
+// Warp roles (576 threads): warps 0-15 frame warps (A producer + epilogue; warp w serves rows 32·(w & 3) … +31 — its
+// TMEM lane quarter — and column quarter q = w >> 2 of every k-tile, so four warps per scheduler hide each other's
+// latencies), warp 16 MMA issuer and TMEM allocator, warp 17 B loader.  Pipelines: A ring (3 stages in TMEM, fed through
+// a 4-deep cp.async ring in shared memory), B ring (6 stages in shared memory), accumulator ring (2).
 constexpr int kTcFrames = 128;
-constexpr int kTcThreads = 192;
+constexpr int kTcFrameWarps = 16;
+constexpr int kTcThreads = (kTcFrameWarps + 2) * 32;     // 576
 constexpr int kTcAStages = 3;
 constexpr int kTcBStages = 6;
 constexpr int kTcACols = 2 * kTcKT;                      // hi + lo columns of one A stage
 constexpr int kTcAccCol0 = kTcAStages * kTcACols;        // 192
 constexpr int kTcAccN = 2 * kTcN;                        // accumulator columns: [A·Bh | A·Bl]
 constexpr int kTcTmemCols = 512;                         // 192 (A ring) + 2 × 160 (accumulators)
-
-constexpr int kTcAPre = 4;  // k-tiles of A rows in flight per frame thread (cp.async ring in shared memory)
+constexpr int kTcAPre = 4;                               // k-tiles of A rows in flight (cp.async ring in shared memory)
 
 struct TcSmem {
     alignas(1024) unsigned char b[kTcBStages][kTcBStageBytes];
     float4 arow[kTcAPre][8][kTcFrames];  // [slot][16-byte chunk][frame]: conflict-free for cp.async and LDS.128
+    float chroma_part[kTcFrames][16];    // [frame][4·q + j]: partial chroma (3q + j) mod 12 of column quarter q
     alignas(8) uint64_t full_a[kTcAStages], empty_a[kTcAStages], full_b[kTcBStages], empty_b[kTcBStages];
     uint64_t acc_full[2], acc_empty[2];
     uint32_t tmem_base;
     double red[4][kChroma];
 };
 
-__device__ __forceinline__ void tc_load_row32(const float *__restrict__ y, int64_t pos, int len, float (&x)[32]) {
-    if (pos >= 0 && pos + 32 <= (int64_t)len && ((reinterpret_cast<uintptr_t>(y + pos) & 15u) == 0)) {
-        const float4 *p = reinterpret_cast<const float4 *>(y + pos);
+__device__ __forceinline__ void tc_load_row8(const float *__restrict__ y, int64_t pos, int len, float (&x)[8]) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float4 v = __ldg(p + i);
-            x[4 * i] = v.x;
-            x[4 * i + 1] = v.y;
-            x[4 * i + 2] = v.z;
-            x[4 * i + 3] = v.w;
-        }
-    } else {
+    for (int i = 0; i < 8; ++i) {
+        const int64_t q = pos + i;
+        x[i] = (q >= 0 && q < len) ? __ldg(y + q) : 0.0f;
+    }
+}
+
+// Epilogue share of column quarter Q: CQT bins b = 9Q … 9Q+8 of this thread's frame.  Accumulator columns: b and 36+b
+// (real / imaginary part of A·Bh), 80+b and 116+b (the same for A·Bl).  Bin b feeds chroma ((b + 1) mod 36) / 3, i.e.
+// acc[j] collects chroma (3Q + j) mod 12, j = 0..3.
+template <int Q>
+__device__ __forceinline__ void tc_epilogue_quarter(uint32_t acc_addr, float (&part)[4]) {
+    using namespace tc05;
+    float re[9], im[9];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const int64_t q = pos + i;
-            x[i] = (q >= 0 && q < len) ? __ldg(y + q) : 0.0f;
+    for (int i = 0; i < 9; ++i) re[i] = im[i] = 0.0f;
+    uint32_t v[16];
+#pragma unroll
+    for (int piece = 0; piece < 4; ++piece) {
+        constexpr int kBase[4] = {0, kCqtBins, kTcN, kTcN + kCqtBins};
+        const int c0 = kBase[piece] + 9 * Q;
+        const int start = c0 & ~7;  // 8-column aligned 16-column load covers c0 … c0+8
+        tmem_ld16(acc_addr + (uint32_t)start, v);
+        wait_ld();
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            const float val = __uint_as_float(v[c0 - start + i]);
+            if (piece & 1) im[i] += val; else re[i] += val;
         }
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        const int b = 9 * Q + i;
+        const int ch = ((b + 1) % kCqtBins) / 3;
+        const int j = (ch - 3 * Q + kChroma) % kChroma;  // 0..3
+        part[j] += sqrtf(re[i] * re[i] + im[i] * im[i]);
     }
 }
 
@@ -739,7 +761,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
 
     if (tid == 0) {
         for (int i = 0; i < kTcAStages; ++i) {
-            mbar_init(&sm.full_a[i], 4);  // one arrival per frame warp
+            mbar_init(&sm.full_a[i], kTcFrameWarps);  // one arrival per frame warp
             mbar_init(&sm.empty_a[i], 1);
         }
         for (int i = 0; i < kTcBStages; ++i) {
@@ -748,11 +770,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&sm.acc_full[i], 1);
-            mbar_init(&sm.acc_empty[i], 4);
+            mbar_init(&sm.acc_empty[i], kTcFrameWarps);
         }
         fence_mbar_init();
     }
-    if (warp == 4) tmem_alloc(&sm.tmem_base, kTcTmemCols);
+    if (warp == kTcFrameWarps) tmem_alloc(&sm.tmem_base, kTcTmemCols);
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
@@ -763,49 +785,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
     constexpr int kKTiles = kCqtNfft / kTcKT;  // 32
     constexpr int kIters = kOctaves * kKTiles;
 
-    if (warp < 4) {
+    if (warp < kTcFrameWarps) {
         // ===================== frame warps: A producer + epilogue =====================
-        const int f = tid;  // row of the tile = TMEM lane
-        const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
+        const int rg = warp & 3, q = warp >> 2;
+        const int f = 32 * rg + lane;  // row of the tile = TMEM lane
+        const uint32_t lane_base = (uint32_t)(32 * rg) << 16;
         const float *pseg = pyr + (size_t)seg * po.off[kOctaves];
-        float chroma[kChroma];
-#pragma unroll
-        for (int c = 0; c < kChroma; ++c) chroma[c] = 0.0f;
+        float part[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 
         auto epilogue = [&](int o) {
             const int buf = o & 1;
             mbar_wait(&sm.acc_full[buf], (uint32_t)((o >> 1) & 1));
             fence_after_sync();
-            // columns 0..35 / 36..71: real / imaginary parts of A·Bh; 80..115 / 116..151: the same for A·Bl
-            float re[kCqtBins], im[kCqtBins];
-#pragma unroll
-            for (int b = 0; b < kCqtBins; ++b) re[b] = im[b] = 0.0f;
-            uint32_t v[16];
             const uint32_t acc = tmem + lane_base + (uint32_t)(kTcAccCol0 + buf * kTcAccN);
-#pragma unroll
-            for (int g = 0; g < kTcAccN / 16; ++g) {
-                tmem_ld16(acc + 16 * g, v);
-                wait_ld();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int col = (16 * g + i) % kTcN;
-                    if (col < kCqtBins) re[col] += __uint_as_float(v[i]);
-                    else if (col < 2 * kCqtBins) im[col - kCqtBins] += __uint_as_float(v[i]);
-                }
+            switch (q) {  // warp-uniform
+                case 0: tc_epilogue_quarter<0>(acc, part); break;
+                case 1: tc_epilogue_quarter<1>(acc, part); break;
+                case 2: tc_epilogue_quarter<2>(acc, part); break;
+                default: tc_epilogue_quarter<3>(acc, part); break;
             }
             fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.acc_empty[buf]);
-#pragma unroll
-            for (int b = 0; b < kCqtBins; ++b) {
-                const float m = sqrtf(re[b] * re[b] + im[b] * im[b]);
-                chroma[((b + 1) % kCqtBins) / 3] += m;  // cq_to_chroma: 3 bins per semitone, rolled −1
-            }
         };
 
-        // A rows stream through a per-thread cp.async ring (kTcAPre k-tiles ahead, flat over octaves × k-tiles) so the
-        // global-load latency never sits in front of the tcgen05.st; zero padding outside [0, len) comes from the
-        // src-size (zfill) form — row starts are multiples of 4 samples, so a 16-byte chunk never straddles 0.
+        // A rows stream through a cp.async ring (kTcAPre k-tiles ahead, flat over octaves × k-tiles): thread (f, q) owns
+        // the two 16-byte chunks 2q, 2q+1 of row f in every k-tile.  Zero padding outside [0, len) comes from the
+        // src-size (zfill) form — row starts are multiples of 4 samples, so a chunk never straddles 0.
         const float *y0 = audio + seg_off[seg];
         const bool y0_aligned = (reinterpret_cast<uintptr_t>(y0) & 15u) == 0;
         auto issue = [&](int it) {
@@ -813,11 +819,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
             const int hop = 512 >> o;
             const float *y = (o == 0) ? y0 : pseg + po.off[o];
             const int len = level_len(n, o);
-            const int64_t base = (int64_t)(t0 + f) * hop - kCqtNfft / 2 + (int64_t)kt * kTcKT;
-            float4 *slot = &sm.arow[it % kTcAPre][0][f];
+            const int64_t base = (int64_t)(t0 + f) * hop - kCqtNfft / 2 + (int64_t)kt * kTcKT + 8 * q;
+            float4 *slot = &sm.arow[it % kTcAPre][2 * q][f];
             if (o > 0 || y0_aligned) {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
+                for (int c = 0; c < 2; ++c) {
                     const int64_t pos = base + 4 * c;
                     int64_t rem = ((int64_t)len - pos) * 4;
                     const uint32_t bytes = pos < 0 ? 0u : (uint32_t)(rem < 0 ? 0 : (rem > 16 ? 16 : rem));
@@ -827,10 +833,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
                                  : "memory");
                 }
             } else {  // unaligned first level (arbitrary caller offset): plain loads into the same slot
-                float xr[32];
-                tc_load_row32(y, base, len, xr);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) slot[c * kTcFrames] = make_float4(xr[4 * c], xr[4 * c + 1], xr[4 * c + 2], xr[4 * c + 3]);
+                float xr[8];
+                tc_load_row8(y, base, len, xr);
+                slot[0] = make_float4(xr[0], xr[1], xr[2], xr[3]);
+                slot[kTcFrames] = make_float4(xr[4], xr[5], xr[6], xr[7]);
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
@@ -842,27 +848,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
             asm volatile("cp.async.wait_group %0;" ::"n"(kTcAPre - 1) : "memory");
             const int o = it >> 5, kt = it & 31;
             const int st = it % kTcAStages;
-            float x[32];
+            uint32_t h[8], l[8];
             {
-                const float4 *slot = &sm.arow[it % kTcAPre][0][f];
+                const float4 *slot = &sm.arow[it % kTcAPre][2 * q][f];
+                const float4 v0 = slot[0], v1 = slot[kTcFrames];
+                const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float4 v = slot[c * kTcFrames];
-                    x[4 * c] = v.x;
-                    x[4 * c + 1] = v.y;
-                    x[4 * c + 2] = v.z;
-                    x[4 * c + 3] = v.w;
+                for (int i = 0; i < 8; ++i) {
+                    const float hi = to_tf32(x[i]);
+                    h[i] = __float_as_uint(hi);
+                    l[i] = __float_as_uint(x[i] - hi);
                 }
             }
-            // split first (pure ALU), so that this work overlaps the landing of the previous tile's tcgen05.st
-            uint32_t h[32], l[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float hi = to_tf32(x[i]);
-                h[i] = __float_as_uint(hi);
-                l[i] = __float_as_uint(x[i] - hi);
-            }
-            if (pending) {  // publish the PREVIOUS tile: one mbarrier arrival per warp
+            if (pending) {  // publish the PREVIOUS tile: its tcgen05.st had a whole iteration to land
                 wait_st();
                 fence_before_sync();
                 __syncwarp();
@@ -870,18 +868,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
             }
             mbar_wait(&sm.empty_a[st], (uint32_t)(((it / kTcAStages) & 1) ^ 1));
             fence_after_sync();
-            const uint32_t a0 = tmem + lane_base + (uint32_t)(st * kTcACols);
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint32_t hv[16], lv[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    hv[i] = h[16 * half + i];
-                    lv[i] = l[16 * half + i];
-                }
-                tmem_st16(a0 + 16 * half, hv);
-                tmem_st16(a0 + kTcKT + 16 * half, lv);
-            }
+            const uint32_t a0 = tmem + lane_base + (uint32_t)(st * kTcACols + 8 * q);
+            tmem_st8(a0, h);
+            tmem_st8(a0 + kTcKT, l);
             pending = true;
             if (kt == kKTiles - 1) {  // octave boundary (and the very last tile): publish before the epilogue
                 wait_st();
@@ -894,23 +883,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
         }
         epilogue(kOctaves - 1);
 
-        // ---- librosa.util.normalize(norm=inf) per frame, then the tile's sum over frames (float64)
-        const bool valid = (t0 + f) < n_frames;
-        float mx = 0.0f;
+        // ---- combine the four column quarters of every frame, librosa.util.normalize(norm=inf) per frame, then the
+        // tile's sum over frames (float64)
 #pragma unroll
-        for (int c = 0; c < kChroma; ++c) mx = fmaxf(mx, chroma[c]);
-        const double len_ = (mx < 1.17549435e-38f) ? 1.0 : (double)mx;
+        for (int j = 0; j < 4; ++j) sm.chroma_part[f][4 * q + j] = part[j];
+        asm volatile("bar.sync 1, 512;" ::: "memory");  // the sixteen frame warps only
+        if (q == 0) {
+            float chroma[kChroma];
 #pragma unroll
-        for (int c = 0; c < kChroma; ++c) {
-            double v = valid ? (double)chroma[c] / len_ : 0.0;
-            v = warp_sum(v);
-            if (lane == 0) sm.red[warp][c] = v;
+            for (int c = 0; c < kChroma; ++c) {
+                // chroma c = slot j = c % 3 of quarter c / 3, plus slot 3 of the previous quarter when c % 3 == 0
+                float v = sm.chroma_part[f][4 * (c / 3) + (c % 3)];
+                if (c % 3 == 0) v += sm.chroma_part[f][4 * ((c / 3 + 3) % 4) + 3];
+                chroma[c] = v;
+            }
+            const bool valid = (t0 + f) < n_frames;
+            float mx = 0.0f;
+#pragma unroll
+            for (int c = 0; c < kChroma; ++c) mx = fmaxf(mx, chroma[c]);
+            const double len_ = (mx < 1.17549435e-38f) ? 1.0 : (double)mx;
+#pragma unroll
+            for (int c = 0; c < kChroma; ++c) {
+                double v = valid ? (double)chroma[c] / len_ : 0.0;
+                v = warp_sum(v);
+                if (lane == 0) sm.red[rg][c] = v;
+            }
+            asm volatile("bar.sync 2, 128;" ::: "memory");  // warps 0-3
+            if (tid < kChroma)
+                partial[((size_t)seg * tile_stride + blockIdx.x) * kChroma + tid] =
+                    ((sm.red[0][tid] + sm.red[1][tid]) + sm.red[2][tid]) + sm.red[3][tid];
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four frame warps only
-        if (tid < kChroma)
-            partial[((size_t)seg * tile_stride + blockIdx.x) * kChroma + tid] =
-                ((sm.red[0][tid] + sm.red[1][tid]) + sm.red[2][tid]) + sm.red[3][tid];
-    } else if (warp == 4) {
+    } else if (warp == kTcFrameWarps) {
         // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
         constexpr uint32_t idesc = idesc_tf32(kTcFrames, kTcAccN);
         for (int o = 0; o < kOctaves; ++o) {
@@ -955,7 +958,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == kTcFrameWarps) {
         fence_after_sync();
         tmem_dealloc(tmem, kTcTmemCols);
     }
