@@ -784,6 +784,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
     tj = tj < 0 ? 0 : (tj >= kNTunings ? kNTunings - 1 : tj);
     constexpr int kKTiles = kCqtNfft / kTcKT;  // 32
     constexpr int kIters = kOctaves * kKTiles;
+    // Every CTA walks the 32 k-tiles of the contraction from a different starting tile: all CTAs of a launch read the
+    // same few B images, and in lock step they would all hit the same L2 lines at the same time.
+    const int kshift = (int)((blockIdx.x * 5u + blockIdx.y * 11u) & (kKTiles - 1));
 
     if (warp < kTcFrameWarps) {
         // ===================== frame warps: A producer + epilogue =====================
@@ -815,7 +818,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
         const float *y0 = audio + seg_off[seg];
         const bool y0_aligned = (reinterpret_cast<uintptr_t>(y0) & 15u) == 0;
         auto issue = [&](int it) {
-            const int o = it >> 5, kt = it & 31;
+            const int o = it >> 5, kt = ((it & 31) + kshift) & 31;
             const int hop = 512 >> o;
             const float *y = (o == 0) ? y0 : pseg + po.off[o];
             const int len = level_len(n, o);
@@ -947,7 +950,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
         // ===================== B loader (warp-uniform, one elected lane issues the bulk copy) =====================
         const unsigned char *src = reinterpret_cast<const unsigned char *>(Bimg) + (size_t)tj * kKTiles * kTcBStageBytes;
         for (int it = 0; it < kIters; ++it) {
-            const int sb = it % kTcBStages, kt = it % kKTiles;
+            const int sb = it % kTcBStages, kt = ((it % kKTiles) + kshift) & (kKTiles - 1);
             mbar_wait(&sm.empty_b[sb], (uint32_t)(((it / kTcBStages) & 1) ^ 1));
             if (elect_one()) {
                 mbar_arrive_expect_tx(&sm.full_b[sb], kTcBStageBytes);
