@@ -41,6 +41,16 @@ def load_peaks():
         return 6650.0, "fallback"
 
 
+def load_traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/ncu_traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)[kernel]
+        return int(t["dram_bytes_per_launch"]), t["source"]
+    except Exception:
+        return None, None
+
+
 def make_pairs(n_distinct: int, dur: float):
     from oracle import synth
     pairs = []
@@ -272,6 +282,7 @@ def run_gpu(args):
 
     if rank == 0:
         peak, peak_kind = load_peaks()
+        traffic, traffic_src = load_traffic("stft_logmel_kernel[hop<=128]")
         value = windows / (ms / 1e3)
         line = {
             "metric": "analysis_windows_per_sec", "value": value, "unit": "windows/s",
@@ -288,10 +299,14 @@ def run_gpu(args):
                     "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": roof["gbs"], "peak": peak, "unit": "GB/s",
-                         "frac": roof["gbs"] / peak, "traffic": None, "peak_kind": peak_kind,
-                         "kernel": roof["kernel"], "algorithmic_bytes": roof["bytes"], "kernel_ms": roof["ms"],
-                         "launches": roof["launches"], "fp32_tflops": roof["tflops"],
-                         "fp32_peak_tflops": 74.5, "share_of_step": roof["share"]},
+                         "frac": roof["gbs"] / peak, "traffic": traffic, "peak_kind": peak_kind,
+                         "kernel": roof["kernel"], "launches": roof["launches"],
+                         "algorithmic_bytes_per_launch": roof["bytes_per_launch"],
+                         "ms_per_launch": roof["ms_per_launch"], "traffic_source": traffic_src,
+                         "fp32_tflops": roof["tflops"], "fp32_peak_tflops": 74.5,
+                         "fp32_frac": roof["tflops"] / 74.5, "share_of_step": roof["share"],
+                         "note": "compute bound (AI 249 flop/B vs ridge 11.5): the FP32 fraction is the binding one",
+                         "front_end": roof["front_end"]},
             "kernels": roof["table"],
             "clocks": clk.summary(),
         }

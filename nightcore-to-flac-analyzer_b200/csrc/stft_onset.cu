@@ -156,7 +156,7 @@ extern "C" int ncfa_onset_strength_batched(const float *d_audio, const int64_t *
     {
         const int64_t groups = ((int64_t)n_seg * frames + kWarps - 1) / kWarps;
         const int grid = (int)(groups < n_sm ? groups : n_sm);  // persistent: one CTA per SM
-        ProfScope _p("stft_logmel_kernel", st);
+        ProfScope _p(hop <= 128 ? "stft_logmel_kernel[hop<=128]" : "stft_logmel_kernel[hop>128]", st);
         stft_logmel_kernel<<<grid, kThreads, sizeof(OnsetSmem), st>>>(d_audio, d_seg_off, d_seg_len, n_seg, hop, frames, tb,
                                                                   S, seg_max);
     }

@@ -21,7 +21,7 @@
 
 namespace ncfa {
 
-constexpr int kLagThreads = 128;
+constexpr int kLagThreads = 256;
 constexpr double kReinitRatio = 1e-4;  // re-sum exactly when the frame energy collapses
 
 // x[m], m in [0, n + 2p): envelope padded with np.pad(mode='linear_ramp', end_values=0)

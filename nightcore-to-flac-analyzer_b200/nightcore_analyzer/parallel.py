@@ -74,18 +74,33 @@ FLOP_PER_FRAME = 64.7e3                      # rFFT-2048 + power + sparse mel + 
 
 
 def frontend_roofline(prof: dict, stats: dict) -> dict:
-    """Roofline of the onset front-end (stft_logmel_kernel + flux_kernel, both hops) from one profiled
-    step: achieved GB/s = algorithmic bytes of the step's windows and hop-64 frames / kernel time."""
+    """Roofline of the dominant kernel — the hop-64 launches of ``stft_logmel_kernel`` (the whole-track onset front-end,
+    tempo.py:158) — from one profiled step: achieved GB/s = algorithmic bytes per launch (frames × 260 B) ÷
+    average launch duration (CUDA events on the launching stream).  The hop-512 window launches and ``flux_kernel`` are
+    reported in the per-kernel table and in ``front_end`` (all STFT + flux launches together)."""
     total_ms = sum(v[1] for v in prof.values()) or 1e-9
     table = {k: {"launches": v[0], "ms": round(v[1], 4), "share": round(v[1] / total_ms, 4)}
              for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
-    ms = sum(prof.get(k, (0, 0.0))[1] for k in ("stft_logmel_kernel", "flux_kernel"))
-    launches = sum(prof.get(k, (0, 0.0))[0] for k in ("stft_logmel_kernel", "flux_kernel"))
     windows = stats.get("windows", 0)
     frames64 = stats.get("hop64_frames", 0)
-    nbytes = windows * BYTES_PER_WINDOW + frames64 * BYTES_PER_HOP64_FRAME
-    flops = (windows * 431 + frames64) * FLOP_PER_FRAME
-    ms = max(ms, 1e-9)
-    return {"kernel": "stft_logmel_kernel+flux_kernel (hop 512 windows and hop 64 tracks)", "bytes": int(nbytes),
-            "ms": ms, "launches": launches, "gbs": nbytes / (ms * 1e-3) / 1e9, "tflops": flops / (ms * 1e-3) / 1e12,
-            "share": ms / total_ms, "table": table}
+    k64 = prof.get("stft_logmel_kernel[hop<=128]", (0, 0.0))
+    k512 = prof.get("stft_logmel_kernel[hop>128]", (0, 0.0))
+    flux = prof.get("flux_kernel", (0, 0.0))
+    n64, ms64 = max(k64[0], 1), max(k64[1], 1e-9)
+    bytes64 = frames64 * BYTES_PER_HOP64_FRAME
+    fe_ms = max(k64[1] + k512[1] + flux[1], 1e-9)
+    fe_bytes = windows * BYTES_PER_WINDOW + bytes64
+    return {
+        "kernel": "stft_logmel_kernel, hop-64 whole-track launches",
+        "launches": k64[0],
+        "bytes_per_launch": bytes64 / n64,
+        "ms_per_launch": ms64 / n64,
+        "gbs": bytes64 / (ms64 * 1e-3) / 1e9,
+        "tflops": frames64 * FLOP_PER_FRAME / (ms64 * 1e-3) / 1e12,
+        "share": ms64 / total_ms,
+        "front_end": {"kernels": "stft_logmel_kernel (both hops) + flux_kernel", "ms": fe_ms, "bytes": int(fe_bytes),
+                      "gbs": fe_bytes / (fe_ms * 1e-3) / 1e9,
+                      "tflops": (windows * 431 + frames64) * FLOP_PER_FRAME / (fe_ms * 1e-3) / 1e12,
+                      "share": fe_ms / total_ms},
+        "table": table,
+    }
