@@ -506,11 +506,9 @@ extern "C" int ncfa_bootstrap_ratio_batched(const double *d_a, const int64_t *d_
         int warps = (int)((200 * 1024) / ((size_t)hist_stride * 4));
         warps = warps > 8 ? 8 : (warps < 1 ? 1 : warps);
         const size_t sh = (size_t)warps * hist_stride * 4;
-        static size_t sh_set = 0;
-        if (sh > 48 * 1024 && sh > sh_set) {
-            NCFA_CUDA_OK(cudaFuncSetAttribute(boot_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              200 * 1024 + 64));
-            sh_set = 200 * 1024 + 64;
+        if (sh > 48 * 1024) {
+            int rc = ensure_dynamic_smem((const void *)boot_median_kernel, 200 * 1024 + 64);
+            if (rc) return rc;
         }
         const long long total = (long long)n_jobs * n_boot;
         long long blocks = (total + warps - 1) / warps;

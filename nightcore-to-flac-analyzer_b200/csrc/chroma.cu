@@ -1047,19 +1047,10 @@ extern "C" int ncfa_tuning_estimate_batched(const float *d_audio, const int64_t 
     uint8_t *pk_bin = (uint8_t *)wp;
     wp += align_up(slots, 256);
     int32_t *pk_cnt = (int32_t *)wp;
-    static bool attr_done = false;
-    if (!attr_done) {
-        NCFA_CUDA_OK(cudaFuncSetAttribute(tuning_peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)sizeof(TuningSmem)));
-        attr_done = true;
-    }
+    if ((rc = ensure_dynamic_smem((const void *)tuning_peaks_kernel, sizeof(TuningSmem)))) return rc;
     {
-        static int n_sm = 0;
-        if (n_sm == 0) {
-            int dev = 0;
-            NCFA_CUDA_OK(cudaGetDevice(&dev));
-            NCFA_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        }
+        int n_sm = 0;
+        if ((rc = sm_count(&n_sm))) return rc;
         const int64_t groups = ((int64_t)n_seg * (int64_t)frames + kTunWarps - 1) / kTunWarps;
         const int grid = (int)(groups < n_sm ? groups : n_sm);
         ProfScope _p("tuning_peaks_kernel", st);
@@ -1122,14 +1113,8 @@ extern "C" int ncfa_chroma_mean_batched(const float *d_audio, const int64_t *d_s
         const char *e = getenv("NCFA_CQT_IMPL");
         use_tc = (e && strcmp(e, "simt") == 0) ? 0 : 1;
     }
-    static bool attr_done = false;
-    if (!attr_done) {
-        NCFA_CUDA_OK(cudaFuncSetAttribute(cqt_chroma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)sizeof(CqtSmem)));
-        NCFA_CUDA_OK(cudaFuncSetAttribute(cqt_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)sizeof(TcSmem) + 1024));
-        attr_done = true;
-    }
+    if ((rc = ensure_dynamic_smem((const void *)cqt_chroma_kernel, sizeof(CqtSmem)))) return rc;
+    if ((rc = ensure_dynamic_smem((const void *)cqt_tc_kernel, sizeof(TcSmem) + 1024))) return rc;
     const int tiles = chroma_tiles(max_seg_len);  // partial[] stride (sized for the 32-frame tiles of the SIMT kernel)
     if (use_tc) {
         ProfScope _p("cqt_tc_kernel", st);

@@ -20,6 +20,36 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+static std::mutex g_attr_mu;
+static std::map<std::pair<int, const void *>, size_t> g_dyn_smem;
+static std::map<int, int> g_sm_count;
+
+int ensure_dynamic_smem(const void *func, size_t bytes) {
+    int dev = 0;
+    NCFA_CUDA_OK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_attr_mu);
+    size_t &cur = g_dyn_smem[std::make_pair(dev, func)];
+    if (bytes > cur) {
+        NCFA_CUDA_OK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        cur = bytes;
+    }
+    return NCFA_OK;
+}
+
+int sm_count(int *out) {
+    int dev = 0;
+    NCFA_CUDA_OK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_attr_mu);
+    auto it = g_sm_count.find(dev);
+    if (it == g_sm_count.end()) {
+        int n = 0;
+        NCFA_CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+        it = g_sm_count.emplace(dev, n).first;
+    }
+    *out = it->second;
+    return NCFA_OK;
+}
+
 // ---- per-kernel event profiler
 struct ProfEntry {
     const char *name;

@@ -38,6 +38,11 @@ void set_error(const char *fmt, ...);
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Thread-safe, monotonic cudaFuncAttributeMaxDynamicSharedMemorySize (host threads on different streams share kernels).
+int ensure_dynamic_smem(const void *func, size_t bytes);
+// SM count of the current device (cached)
+int sm_count(int *out);
+
 // Optional per-kernel timing (ncfa_profile_enable): a ProfScope around a launch records two CUDA
 // events on the launch stream; ncfa_profile_report() synchronises them and sums per kernel name.
 bool prof_enabled();

@@ -143,16 +143,9 @@ extern "C" int ncfa_onset_strength_batched(const float *d_audio, const int64_t *
     float *S = (float *)d_workspace;
     unsigned *seg_max = (unsigned *)((char *)d_workspace + align_up((size_t)n_seg * frames * NCFA_N_MELS * 4, 256));
     NCFA_CUDA_OK(cudaMemsetAsync(seg_max, 0, (size_t)n_seg * 4, st));
-    static bool attr_done = false;
-    static int n_sm = 0;
-    if (!attr_done) {
-        NCFA_CUDA_OK(cudaFuncSetAttribute(stft_logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)sizeof(OnsetSmem)));
-        int dev = 0;
-        NCFA_CUDA_OK(cudaGetDevice(&dev));
-        NCFA_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        attr_done = true;
-    }
+    int n_sm = 0;
+    if ((rc = ensure_dynamic_smem((const void *)stft_logmel_kernel, sizeof(OnsetSmem)))) return rc;
+    if ((rc = sm_count(&n_sm))) return rc;
     {
         const int64_t groups = ((int64_t)n_seg * frames + kWarps - 1) / kWarps;
         const int grid = (int)(groups < n_sm ? groups : n_sm);  // persistent: one CTA per SM

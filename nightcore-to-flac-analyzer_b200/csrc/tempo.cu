@@ -396,10 +396,9 @@ extern "C" int ncfa_tempo_lag_batched(const float *d_onset, const int64_t *d_ons
         dim3 g((max_env_len + per_cta - 1) / per_cta, n_seg);
         const int span_max = (max_env_len < per_cta ? max_env_len : per_cta) + W;
         size_t sh = (size_t)(span_max + (span_max >> 5) + 2) * 8;
-        static size_t sh_set0 = 0;
-        if (sh > 48 * 1024 && sh > sh_set0) {
-            NCFA_CUDA_OK(cudaFuncSetAttribute(tg_r0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-            sh_set0 = sh;
+        if (sh > 48 * 1024) {
+            int rc = ensure_dynamic_smem((const void *)tg_r0_kernel, sh);
+            if (rc) return rc;
         }
         {
             ProfScope _p("tg_r0_kernel", st);
@@ -414,10 +413,9 @@ extern "C" int ncfa_tempo_lag_batched(const float *d_onset, const int64_t *d_ons
     NCFA_LAUNCH_OK("tg_range_kernel");
     {
         size_t sh = (size_t)(chunk + W) * 8;
-        static size_t sh_set = 0;
-        if (sh > 48 * 1024 && sh > sh_set) {
-            NCFA_CUDA_OK(cudaFuncSetAttribute(tg_lag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-            sh_set = sh;
+        if (sh > 48 * 1024) {
+            int rc = ensure_dynamic_smem((const void *)tg_lag_kernel, sh);
+            if (rc) return rc;
         }
         dim3 g((W - k_min + kLagThreads - 1) / kLagThreads, n_chunks, n_seg);
         {

@@ -444,10 +444,19 @@ _ENG_LOCK = threading.Lock()
 
 
 def get_engine(device=None) -> Engine:
+    """The calling thread's engine for `device` (workspaces are per engine, so concurrent host threads — each on its own
+    CUDA stream — never share scratch buffers)."""
     if not torch.cuda.is_available():
         raise _native.NcfaError("nightcore_analyzer needs a CUDA device (sm_100a); there is no CPU fallback")
     idx = torch.cuda.current_device() if device is None else torch.device(device).index or 0
+    key = (idx, threading.get_ident())
     with _ENG_LOCK:
-        if idx not in _ENGINES:
-            _ENGINES[idx] = Engine(torch.device("cuda", idx))
-        return _ENGINES[idx]
+        if key not in _ENGINES:
+            _ENGINES[key] = Engine(torch.device("cuda", idx))
+        return _ENGINES[key]
+
+
+def total_launches() -> int:
+    """Kernels launched by every engine of this process (bench.py's gpu_launches)."""
+    with _ENG_LOCK:
+        return sum(e.launches for e in _ENGINES.values())

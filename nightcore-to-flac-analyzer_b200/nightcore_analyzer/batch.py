@@ -283,46 +283,77 @@ def run_batch_arrays(pairs: Sequence[Tuple[np.ndarray, np.ndarray]], sr: int = S
     return analyse_staged(stage_pairs(pairs, sr), **kwargs)
 
 
-def analyse_pinned(pb: PinnedBatch, sizes: Sequence[int], stats: Optional[dict] = None, **kwargs):
-    """End-to-end form of the batch scheduler: the pairs of a pinned host batch are analysed in sub-batches of
-    ``sizes`` pairs each (every sub-batch reads the first ``k`` pairs of ``pb`` — bench.py tiles one composition), and
-    the pinned→HBM copy of sub-batch i+1 runs on a second stream while sub-batch i is analysed."""
+def run_subbatches(jobs: Sequence, fn, workers: int = 2) -> list:
+    """Run ``fn(job)`` for every job on ``workers`` host threads, each with its own CUDA stream and engine, and return
+    the results in job order.  While one thread waits for a device→host read or assembles results, the other keeps the
+    GPU fed; uploads issued by one thread overlap the kernels of the other."""
+    import concurrent.futures as cf
     eng = _engine.get_engine()
-    copy_stream = _copy_stream(eng.device)
-    main = torch.cuda.current_stream(eng.device)
-    results: list = []
-    total_h2d = 0
+    device = eng.device
+    main = torch.cuda.current_stream(device)
+    if workers <= 1 or len(jobs) <= 1:
+        return [fn(j) for j in jobs]
+    streams = [_worker_stream(device, w) for w in range(workers)]
+    for st in streams:
+        st.wait_stream(main)
+    out: list = [None] * len(jobs)
 
-    def start_upload(k):
-        copy_stream.wait_stream(main)          # the buffer the allocator hands out may have been used on `main`
-        with torch.cuda.stream(copy_stream):
-            st = upload(pb, k)
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        return st, ev
+    def work(w: int):
+        torch.cuda.set_device(device)
+        with torch.cuda.stream(streams[w]):
+            for i in range(w, len(jobs), workers):
+                out[i] = fn(jobs[i])
+            streams[w].synchronize()
 
-    nxt = start_upload(sizes[0]) if sizes else None
-    for i, k in enumerate(sizes):
-        cur, ev = nxt
-        main.wait_event(ev)
-        cur.audio.record_stream(main)
-        nxt = start_upload(sizes[i + 1]) if i + 1 < len(sizes) else None
+    with cf.ThreadPoolExecutor(max_workers=workers) as pool:
+        for f in [pool.submit(work, w) for w in range(workers)]:
+            f.result()
+    for st in streams:
+        main.wait_stream(st)
+    return out
+
+
+def analyse_pinned(pb: PinnedBatch, sizes: Sequence[int], stats: Optional[dict] = None, workers: int = 2, **kwargs):
+    """End-to-end form of the batch scheduler: the pairs of a pinned host batch are analysed in sub-batches of
+    ``sizes`` pairs each (every sub-batch reads the first ``k`` pairs of ``pb`` — bench.py tiles one composition).
+    Sub-batches are dealt to ``workers`` host threads / CUDA streams, so the pinned→HBM copy and the host-side stages of
+    one sub-batch overlap the kernels of another."""
+    def one(k):
         s1: dict = {}
-        results += analyse_staged(cur, stats=s1, **kwargs)
-        total_h2d += cur.h2d_bytes
+        st = upload(pb, k)
+        res = analyse_staged(st, stats=s1, **kwargs)
+        s1["h2d_bytes"] = st.h2d_bytes
+        return res, s1
+
+    results: list = []
+    for res, s1 in run_subbatches(list(sizes), one, workers):
+        results += res
         if stats is not None:
             for key, v in s1.items():
                 stats[key] = stats.get(key, 0) + v
-    if stats is not None:
-        stats["h2d_bytes"] = total_h2d
     return results
 
 
-_COPY_STREAMS: dict = {}
+def analyse_resident(batches: Sequence[StagedBatch], stats: Optional[dict] = None, workers: int = 2, **kwargs):
+    """Same scheduler for sub-batches that already live in HBM."""
+    def one(st):
+        s1: dict = {}
+        return analyse_staged(st, stats=s1, **kwargs), s1
+
+    results: list = []
+    for res, s1 in run_subbatches(list(batches), one, workers):
+        results += res
+        if stats is not None:
+            for key, v in s1.items():
+                stats[key] = stats.get(key, 0) + v
+    return results
 
 
-def _copy_stream(device) -> "torch.cuda.Stream":
-    key = torch.device(device).index
-    if key not in _COPY_STREAMS:
-        _COPY_STREAMS[key] = torch.cuda.Stream(device=device)
-    return _COPY_STREAMS[key]
+_WORKER_STREAMS: dict = {}
+
+
+def _worker_stream(device, w: int) -> "torch.cuda.Stream":
+    key = (torch.device(device).index, w)
+    if key not in _WORKER_STREAMS:
+        _WORKER_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _WORKER_STREAMS[key]
