@@ -283,31 +283,53 @@ def run_batch_arrays(pairs: Sequence[Tuple[np.ndarray, np.ndarray]], sr: int = S
     return analyse_staged(stage_pairs(pairs, sr), **kwargs)
 
 
-def run_subbatches(jobs: Sequence, fn, workers: int = 2) -> list:
-    """Run ``fn(job)`` for every job on ``workers`` host threads, each with its own CUDA stream and engine, and return
+def run_subbatches(jobs: Sequence, fn, workers: int = 2, prepare=None) -> list:
+    """Run ``fn(x)`` for every job on ``workers`` host threads, each with its own CUDA stream and engine, and return
     the results in job order.  While one thread waits for a device→host read or assembles results, the other keeps the
-    GPU fed; uploads issued by one thread overlap the kernels of the other."""
+    GPU fed.  With ``prepare`` (job → StagedBatch, an H2D upload) each worker stages its NEXT job on a separate copy
+    stream before it analyses the current one, so copies never sit in front of kernels."""
     import concurrent.futures as cf
     eng = _engine.get_engine()
     device = eng.device
     main = torch.cuda.current_stream(device)
-    if workers <= 1 or len(jobs) <= 1:
-        return [fn(j) for j in jobs]
+    workers = max(1, min(workers, len(jobs)))
     streams = [_worker_stream(device, w) for w in range(workers)]
-    for st in streams:
+    copies = [_worker_stream(device, 100 + w) for w in range(workers)]
+    for st in streams + copies:
         st.wait_stream(main)
     out: list = [None] * len(jobs)
 
     def work(w: int):
         torch.cuda.set_device(device)
+        mine = list(range(w, len(jobs), workers))
+
+        def stage(i):
+            if prepare is None:
+                return jobs[i], None
+            copies[w].wait_stream(streams[w])      # the allocator may hand out a block last used by this worker's kernels
+            with torch.cuda.stream(copies[w]):
+                x = prepare(jobs[i])
+                ev = torch.cuda.Event()
+                ev.record(copies[w])
+            return x, ev
+
+        nxt = stage(mine[0]) if mine else None
         with torch.cuda.stream(streams[w]):
-            for i in range(w, len(jobs), workers):
-                out[i] = fn(jobs[i])
+            for n, i in enumerate(mine):
+                x, ev = nxt
+                if ev is not None:
+                    streams[w].wait_event(ev)
+                    x.audio.record_stream(streams[w])
+                nxt = stage(mine[n + 1]) if n + 1 < len(mine) else None
+                out[i] = fn(x)
             streams[w].synchronize()
 
-    with cf.ThreadPoolExecutor(max_workers=workers) as pool:
-        for f in [pool.submit(work, w) for w in range(workers)]:
-            f.result()
+    if workers == 1:
+        work(0)
+    else:
+        with cf.ThreadPoolExecutor(max_workers=workers) as pool:
+            for f in [pool.submit(work, w) for w in range(workers)]:
+                f.result()
     for st in streams:
         main.wait_stream(st)
     return out
@@ -316,17 +338,16 @@ def run_subbatches(jobs: Sequence, fn, workers: int = 2) -> list:
 def analyse_pinned(pb: PinnedBatch, sizes: Sequence[int], stats: Optional[dict] = None, workers: int = 2, **kwargs):
     """End-to-end form of the batch scheduler: the pairs of a pinned host batch are analysed in sub-batches of
     ``sizes`` pairs each (every sub-batch reads the first ``k`` pairs of ``pb`` — bench.py tiles one composition).
-    Sub-batches are dealt to ``workers`` host threads / CUDA streams, so the pinned→HBM copy and the host-side stages of
-    one sub-batch overlap the kernels of another."""
-    def one(k):
+    Sub-batches are dealt to ``workers`` host threads / CUDA streams; every worker uploads its next sub-batch
+    (pinned → HBM, separate copy stream) while it analyses the current one."""
+    def one(st):
         s1: dict = {}
-        st = upload(pb, k)
         res = analyse_staged(st, stats=s1, **kwargs)
         s1["h2d_bytes"] = st.h2d_bytes
         return res, s1
 
     results: list = []
-    for res, s1 in run_subbatches(list(sizes), one, workers):
+    for res, s1 in run_subbatches(list(sizes), one, workers, prepare=lambda k: upload(pb, k)):
         results += res
         if stats is not None:
             for key, v in s1.items():
