@@ -197,7 +197,7 @@ def run_gpu(args):
     # The rank's pairs are analysed in sub-batches (the batch scheduler of DESIGN.md): every sub-batch has the
     # same composition (distinct pairs tiled), so ONE pinned host buffer feeds all of them.
     sub = max(1, min(args.sub_batch, len(my_ids))) if my_ids else 1
-    sizes = [min(sub, len(my_ids) - s) for s in range(0, len(my_ids), sub)]
+    sizes = nbatch.plan_subbatches(len(my_ids), sub, args.workers)
     pairs_sub = [distinct[j % len(distinct)] for j in range(sub)]
     pinned = nbatch.pin_pairs(pairs_sub, SR)
     resident = [nbatch.upload(pinned, k) for k in sizes]       # `value`: inputs already in HBM

@@ -283,6 +283,23 @@ def run_batch_arrays(pairs: Sequence[Tuple[np.ndarray, np.ndarray]], sr: int = S
     return analyse_staged(stage_pairs(pairs, sr), **kwargs)
 
 
+def plan_subbatches(n_pairs: int, sub: int, workers: int = 2) -> List[int]:
+    """Sub-batch sizes for ``n_pairs`` pairs: full sub-batches of ``sub`` pairs, preceded by one quarter-size sub-batch
+    per worker so that the first kernels start after a short upload instead of a full one (the head of the pipeline
+    is the only part of the H2D traffic that cannot overlap compute)."""
+    sizes: List[int] = []
+    left = int(n_pairs)
+    head = max(1, sub // 4)
+    for _ in range(workers):
+        if left > sub:
+            sizes.append(min(head, left))
+            left -= sizes[-1]
+    while left > 0:
+        sizes.append(min(sub, left))
+        left -= sizes[-1]
+    return sizes
+
+
 def run_subbatches(jobs: Sequence, fn, workers: int = 2, prepare=None) -> list:
     """Run ``fn(x)`` for every job on ``workers`` host threads, each with its own CUDA stream and engine, and return
     the results in job order.  While one thread waits for a device→host read or assembles results, the other keeps the
