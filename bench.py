@@ -198,7 +198,8 @@ def run_gpu(args):
     # same composition (distinct pairs tiled), so ONE pinned host buffer feeds all of them.
     sub = max(1, min(args.sub_batch, len(my_ids))) if my_ids else 1
     sizes = [min(sub, len(my_ids) - s) for s in range(0, len(my_ids), sub)]        # resident sub-batches
-    sizes_e2e = nbatch.plan_subbatches(len(my_ids), sub, args.workers)           # short head: first kernels start early
+    sub_e2e = min(sub, max(16, -(-len(my_ids) // 4)))                            # at least ~4 pieces per rank
+    sizes_e2e = nbatch.plan_subbatches(len(my_ids), sub_e2e, args.workers)       # short head: first kernels start early
     pairs_sub = [distinct[j % len(distinct)] for j in range(sub)]
     pinned = nbatch.pin_pairs(pairs_sub, SR)
     resident = [nbatch.upload(pinned, k) for k in sizes]       # `value`: inputs already in HBM
@@ -288,7 +289,7 @@ def run_gpu(args):
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": f"synthetic ({len(distinct)} distinct pairs tiled to {total_pairs}; oracle/synth.py)",
             "config": {"workload": WORKLOAD, "pairs": total_pairs, "pair_sec": args.pair_sec, "sr": SR,
-                       "sub_batch_pairs": sub, "host_workers": args.workers, "windows_per_step": windows, "pairs_ok": n_ok,
+                       "sub_batch_pairs": sub, "e2e_sub_batches": sizes_e2e, "host_workers": args.workers, "windows_per_step": windows, "pairs_ok": n_ok,
                        "pitch": not args.no_pitch, "ibi": not args.no_ibi,
                        "l2": "inputs larger than L2 (resident audio per rank %.0f MB > 126 MB)" % (resident_bytes / 1e6)
                        if resident_bytes > (126 << 20) else "inputs smaller than L2 (reduced --pairs run)"},
