@@ -60,21 +60,9 @@ static bool g_prof_on = false;
 static std::vector<ProfEntry> g_prof;
 
 bool prof_enabled() { return g_prof_on; }
-void prof_record(const char *name, cudaStream_t st, bool begin) {
+void prof_commit(const char *name, cudaEvent_t e0, cudaEvent_t e1) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
-    if (begin) {
-        ProfEntry e{name, nullptr, nullptr};
-        cudaEventCreate(&e.e0);
-        cudaEventCreate(&e.e1);
-        cudaEventRecord(e.e0, st);
-        g_prof.push_back(e);
-    } else {
-        for (size_t i = g_prof.size(); i-- > 0;)
-            if (g_prof[i].name == name) {
-                cudaEventRecord(g_prof[i].e1, st);
-                break;
-            }
-    }
+    g_prof.push_back(ProfEntry{name, e0, e1});
 }
 
 // ---- Slaney mel scale (librosa.filters.mel(htk=False, norm='slaney'))
@@ -226,6 +214,8 @@ extern "C" int ncfa_profile_report(char *buf, size_t cap) {
             auto &a = acc[e.name];
             a.first += 1;
             a.second += ms;
+        } else {
+            (void)cudaGetLastError();  // never leave a stale error behind for the caller's next CUDA check
         }
         cudaEventDestroy(e.e0);
         cudaEventDestroy(e.e1);

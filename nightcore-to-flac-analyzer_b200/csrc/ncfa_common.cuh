@@ -43,19 +43,24 @@ int ensure_dynamic_smem(const void *func, size_t bytes);
 // SM count of the current device (cached)
 int sm_count(int *out);
 
-// Optional per-kernel timing (ncfa_profile_enable): a ProfScope around a launch records two CUDA
-// events on the launch stream; ncfa_profile_report() synchronises them and sums per kernel name.
+// Optional per-kernel timing (ncfa_profile_enable): a ProfScope around a launch records two CUDA events on the launch
+// stream (it owns both, so scopes of concurrent host threads never pair up with each other) and hands them to the
+// registry when it closes; ncfa_profile_report() synchronises them and sums per kernel name.
 bool prof_enabled();
-void prof_record(const char *name, cudaStream_t st, bool begin);
+void prof_commit(const char *name, cudaEvent_t e0, cudaEvent_t e1);
 struct ProfScope {
     const char *name;
     cudaStream_t st;
     bool on;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
     ProfScope(const char *n, cudaStream_t s) : name(n), st(s), on(prof_enabled()) {
-        if (on) prof_record(name, st, true);
+        if (on) {
+            on = cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess &&
+                 cudaEventRecord(e0, st) == cudaSuccess;
+        }
     }
     ~ProfScope() {
-        if (on) prof_record(name, st, false);
+        if (on && cudaEventRecord(e1, st) == cudaSuccess) prof_commit(name, e0, e1);
     }
 };
 
