@@ -246,8 +246,10 @@ def run_gpu(args):
 
     # ---- per-kernel shares and the front-end roofline: one extra step with the library's event profiler on
     from nightcore_analyzer import _native
+    # (single host worker here: with two streams the event brackets of one stream would include the other's kernels)
     _native.lib.ncfa_profile_enable(1)
-    _, pstats = step_resident()
+    pstats = {}
+    nbatch.analyse_resident(resident, stats=pstats, workers=1, **kw)
     torch.cuda.synchronize()
     prof = _native.profile_report()
     _native.lib.ncfa_profile_enable(0)

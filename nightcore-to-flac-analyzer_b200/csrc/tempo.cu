@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(256) tg_argmax_kernel(const float *__restrict_
     if (threadIdx.x == 0) lag_out[seg] = (s_idx[0] == 0x7fffffff) ? k_min : s_idx[0];
 }
 
-static int tempo_chunk(int max_env_len) { return max_env_len <= 1024 ? (max_env_len < 1 ? 1 : max_env_len) : 2048; }
+static int tempo_chunk(int max_env_len) { return max_env_len <= 1024 ? (max_env_len < 1 ? 1 : max_env_len) : 4096; }
 
 }  // namespace ncfa
 

@@ -551,3 +551,50 @@ def chroma_cqt(y: np.ndarray, sr: float = 22050, hop_length: int = 512, bins_per
     chroma = cq_to_chroma(C.shape[0], bins_per_octave, n_chroma).dot(C)
     chroma[chroma < 0.0] = 0.0
     return _normalize_inf(chroma, axis=0)
+
+
+# --------------------------------------------------------------------------- spectral statistics (spectral.py:38-103)
+
+
+def fft_frequencies(sr: float = 22050, n_fft: int = 2048) -> np.ndarray:
+    """librosa.fft_frequencies = np.fft.rfftfreq(n_fft, 1/sr)."""
+    return np.fft.rfftfreq(n=n_fft, d=1.0 / sr)
+
+
+def _normalize_l1(S: np.ndarray, axis: int) -> np.ndarray:
+    """librosa.util.normalize(norm=1, fill=None): divide by the sum of magnitudes; columns below tiny stay unscaled."""
+    mag = np.abs(S).astype(float)
+    length = np.sum(mag, axis=axis, keepdims=True)
+    length[length < tiny(S)] = 1.0
+    return S / length
+
+
+def spectral_centroid(y: np.ndarray, sr: float = 22050, n_fft: int = 2048, hop_length: int = 512) -> np.ndarray:
+    """librosa.feature.spectral_centroid(y=, sr=) → [1, n_frames]: sum(freq · normalize(|STFT|, norm=1))."""
+    S = np.abs(stft(np.asarray(y, dtype=np.float32), n_fft=n_fft, hop_length=hop_length))
+    freq = fft_frequencies(sr, n_fft)
+    return np.sum(freq[:, None] * _normalize_l1(S, axis=0), axis=0, keepdims=True)
+
+
+def spectral_rolloff(y: np.ndarray, sr: float = 22050, n_fft: int = 2048, hop_length: int = 512,
+                     roll_percent: float = 0.85) -> np.ndarray:
+    """librosa.feature.spectral_rolloff → [1, n_frames]: lowest bin frequency whose cumulative magnitude reaches
+    roll_percent of the frame total."""
+    S = np.abs(stft(np.asarray(y, dtype=np.float32), n_fft=n_fft, hop_length=hop_length))
+    freq = fft_frequencies(sr, n_fft)[:, None]
+    total_energy = np.cumsum(S, axis=0)
+    threshold = roll_percent * total_energy[-1]
+    ind = np.where(total_energy < threshold[None, :], np.nan, 1)
+    return np.nanmin(ind * freq, axis=0, keepdims=True)
+
+
+def amplitude_to_db(S: np.ndarray, ref=1.0, amin: float = 1e-5, top_db: float = 80.0) -> np.ndarray:
+    """librosa.amplitude_to_db(S, ref=np.max) = power_to_db(S², ref=ref², amin=amin², top_db)."""
+    magnitude = np.abs(S)
+    ref_value = ref(magnitude) if callable(ref) else np.abs(ref)
+    power = np.square(magnitude)
+    log_spec = 10.0 * np.log10(np.maximum(amin ** 2, power))
+    log_spec = log_spec - 10.0 * np.log10(np.maximum(amin ** 2, ref_value ** 2))
+    if top_db is not None:
+        log_spec = np.maximum(log_spec, log_spec.max() - top_db)
+    return log_spec

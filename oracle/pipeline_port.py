@@ -292,3 +292,28 @@ def content_offset(src_audio: np.ndarray, nc_audio: np.ndarray, sr: int, speed_l
         if score > best[0]:
             best = (score, pk * hop_sec, speed)
     return ((best[1], best[2]), dbg) if return_debug else (best[1], best[2])
+
+
+# ---------------------------------------------------------------------------------------------- spectral.py
+def spectral_stats(y: np.ndarray, sr: int) -> dict:
+    """spectral.analyze (spectral.py:54-103) from the point where the file is loaded at its native rate."""
+    y = np.asarray(y, dtype=np.float32)
+    centroid = float(np.mean(lr.spectral_centroid(y, sr)))
+    rolloff = float(np.mean(lr.spectral_rolloff(y, sr, roll_percent=0.85)))
+    rms = lr.rms(y, 2048, 512)
+    stft = np.abs(lr.stft(y))
+    freqs = lr.fft_frequencies(sr)
+
+    def band(lo, hi):
+        mask = (freqs >= lo) & (freqs < hi)
+        return float(np.mean(stft[mask, :])) if mask.any() else 0.0
+
+    loud = rms[rms > np.percentile(rms, 75)]
+    stft_db = lr.amplitude_to_db(stft, ref=np.max)
+    freq_avg_db = np.mean(stft_db, axis=1)
+    significant = freq_avg_db > (np.max(freq_avg_db) - 60.0)
+    bw = float(freqs[np.where(significant)[0][-1]]) if significant.any() else float(freqs[-1])
+    return dict(centroid=centroid, rolloff=rolloff, rms_mean=float(np.mean(rms)), rms_variance=float(np.var(rms)),
+                sub_bass=band(20, 80), bass=band(80, 250), midrange=band(250, 2000), presence=band(2000, 6000),
+                brilliance=band(6000, 20000), decay_rate=float(np.mean(np.diff(loud))) if len(loud) > 1 else 0.0,
+                duration=len(y) / float(sr), effective_bandwidth_hz=bw, freq_avg_db=freq_avg_db)
