@@ -168,6 +168,16 @@ int ncfa_align_search(const double *d_src_env, int n_src, const double *d_nc_env
                       int max_lags, int32_t *d_peak_idx, double *d_score, void *d_workspace, size_t workspace_bytes,
                       void *stream);
 
+/* ---- spectral.py:54-96 spectral.analyze: whole-file statistics of |STFT(2048, 512, Hann)| --------
+ * d_stats[16·i + s]: s = 0 Σ_frames spectral_centroid (Hz), 1 Σ_frames spectral_rolloff(0.85) (Hz), 2..6 Σ of |STFT| over
+ * the bins of the bands 20–80, 80–250, 250–2000, 2000–6000, 6000–20000 Hz and all frames, 7 number of frames,
+ * 8 max |STFT|.  d_bin_db_mean[1025·i + k] = mean over frames of amplitude_to_db(|STFT|, ref=max, top_db=80)[k].
+ * Means are formed by the caller (centroid / frames, band sum / (bins·frames)). */
+size_t ncfa_spectral_workspace_bytes(int n_seg);
+int ncfa_spectral_stats_batched(const float *d_audio, const int64_t *d_seg_off, const int32_t *d_seg_len, int n_seg, int sr,
+                                double *d_stats, float *d_bin_db_mean, void *d_workspace, size_t workspace_bytes,
+                                void *stream);
+
 /* Host-side constant-table builders (no GPU needed; used by the CPU test-suite):
  * h_K[1024][72] = the CQT contraction matrix of tuning index j; h_taps[127] = the half-band FIR. */
 int ncfa_host_cqt_matrix(int sr, int tuning_index, float *h_K);

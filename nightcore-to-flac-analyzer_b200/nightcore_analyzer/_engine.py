@@ -400,6 +400,23 @@ class Engine:
         self.launches += 3
         return self.to_host(pk), self.to_host(sc)
 
+    # ------------------------------------------------------------------ spectral.py: whole-file STFT statistics
+    def spectral_stats_dev(self, audio: torch.Tensor, seg_off: np.ndarray, seg_len: np.ndarray, sr: int):
+        """→ (stats float64 [n_seg, 16], bin_db_mean float32 [n_seg, 1025]) on the device (layout: include/ncfa.h)."""
+        n_seg = len(seg_len)
+        stats = torch.zeros((max(n_seg, 1), 16), dtype=torch.float64, device=self.device)
+        bins = torch.zeros((max(n_seg, 1), 1025), dtype=torch.float32, device=self.device)
+        if n_seg == 0:
+            return stats[:0], bins[:0]
+        d_off, d_len = self.to_dev(seg_off.astype(np.int64)), self.to_dev(seg_len.astype(np.int32))
+        with torch.cuda.device(self.device):
+            ws = self.workspace("spectral", lib.ncfa_spectral_workspace_bytes(n_seg))
+            check(lib.ncfa_spectral_stats_batched(_ptr(audio), _ptr(d_off), _ptr(d_len), n_seg, int(sr), _ptr(stats),
+                                                  _ptr(bins), _ptr(ws), ws.numel(), self._stream()),
+                  "ncfa_spectral_stats_batched")
+        self.launches += 4
+        return stats[:n_seg], bins[:n_seg]
+
     # ------------------------------------------------------------------ host conveniences
     def onset_strength(self, arrays: Sequence[np.ndarray], hop: int, sr: int) -> List[np.ndarray]:
         audio, off, ln = self.pack(arrays)

@@ -64,6 +64,8 @@ _SIGNATURES = {
     "ncfa_f32_to_f64": (c_int, [_P, c_int64, _P, _P]),
     "ncfa_align_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "ncfa_align_search": (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P]),
+    "ncfa_spectral_workspace_bytes": (c_size_t, [c_int]),
+    "ncfa_spectral_stats_batched": (c_int, [_P, _P, _P, c_int, c_int, _P, _P, _P, c_size_t, _P]),
     "ncfa_host_cqt_matrix": (c_int, [c_int, c_int, _P]),
     "ncfa_host_halfband_taps": (c_int, [_P]),
 }

@@ -75,7 +75,7 @@ def load_audio(path: str, sr: int = SAMPLE_RATE) -> tuple[np.ndarray, int]:
     scipy's polyphase filter (NOT soxr_hq — documented deviation)."""
     path = str(path)
     if path.endswith(".npy"):
-        return np.load(path).astype(np.float32), sr
+        return np.load(path).astype(np.float32), (sr or SAMPLE_RATE)
     with wave.open(path, "rb") as w:
         n, ch, sw, fr = w.getnframes(), w.getnchannels(), w.getsampwidth(), w.getframerate()
         raw = w.readframes(n)
