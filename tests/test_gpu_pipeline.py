@@ -86,3 +86,24 @@ def test_manual_trim_and_no_pitch(engine, pair):
     res = na.run_arrays(pair[0], pair[1], SR, src_trim_sec=2.5, compute_pitch=False, log=None)
     assert res.intro_offset_sec == 2.5 and res.pitch_method is None and res.pitch_ratio == 1.0
     assert res.src_duration < len(pair[1]) / SR - 2.4
+
+
+def test_verification_library_call(engine):
+    """workflow.py:778-833 as a library call — a faithful HQNC passes, a 1.5 % slow one fails on IBI."""
+    import scipy.signal
+    from nightcore_analyzer import verify as nverify
+    src = synth.synth(2100, 60.0, SR, bpm=128.0)
+    ncog = scipy.signal.resample_poly(src, 4, 5).astype(np.float32)
+    ncog = (ncog + np.random.default_rng(3).standard_normal(len(ncog)).astype(np.float32) * 0.003).astype(np.float32)
+    good = scipy.signal.resample_poly(src, 4, 5).astype(np.float32)
+    v = nverify.verify_arrays(good, ncog, SR)
+    w = port.run_arrays(ncog, good, SR, compute_pitch=False, faithful_cost=False)
+    wx = port.speed_xcorr_arrays(good, ncog, SR)
+    assert (v.result.tempo_ratio, v.result.tempo_ci) == w["tempo"]
+    assert (v.result.ibi_ratio, v.result.ibi_ci) == w["ibi"]
+    assert v.result.xcorr_ratio == wx[0] and abs(v.result.xcorr_quality - wx[1]) <= 1e-5
+    assert v.estimator == "IBI" and v.tempo_ok and v.pitch_ok and not v.length_warn
+    slow = scipy.signal.resample_poly(src, 203, 250).astype(np.float32)     # speed 1.2315 instead of 1.25
+    v2 = nverify.verify_arrays(slow, ncog, SR)
+    assert not v2.tempo_ok and v2.length_warn
+    assert abs(v2.corrected_speed_factor - 1.25 / (250 / 203)) < 5e-3
