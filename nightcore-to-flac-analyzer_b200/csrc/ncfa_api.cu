@@ -163,7 +163,6 @@ int get_tables(int sr, Tables *out) {
                 const int m = mel_band_of(q, l);
                 mw = std::max(mw, start[m + 1] - start[m]);
             }
-            mw = (mw + 3) / 4 * 4;  // the kernels walk the weights four at a time (zero padded)
             dt.t.mel_qoff[q] = rows;
             dt.t.mel_qw[q] = mw;
             rows += mw;

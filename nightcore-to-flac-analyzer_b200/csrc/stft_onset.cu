@@ -72,16 +72,9 @@ __global__ void __launch_bounds__(kThreads, 1) stft_logmel_kernel(const float *_
             const float *wt = sm.melwt + (size_t)tb.mel_qoff[q] * 32 + lane;
             const float *pk = pw + b0[q];
             const int nw = tb.mel_qw[q];
-            // zero weights beyond the band's support; four independent chains (nw is a multiple of 4)
-            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-            for (int i = 0; i < nw; i += 4) {
-                a0 = fmaf(wt[i * 32], pk[i], a0);
-                a1 = fmaf(wt[(i + 1) * 32], pk[i + 1], a1);
-                a2 = fmaf(wt[(i + 2) * 32], pk[i + 2], a2);
-                a3 = fmaf(wt[(i + 3) * 32], pk[i + 3], a3);
-            }
-            const float acc = (a0 + a1) + (a2 + a3);
-            const float db = 3.01029995663981195f * __log2f(fmaxf(1e-10f, acc));  // 10·log10(x) on the SFU (abs err < 2e-6 dB)
+            float acc = 0.0f;
+            for (int i = 0; i < nw; ++i) acc = fmaf(wt[i * 32], pk[i], acc);  // zero weights beyond the band's support
+            const float db = 10.0f * log10f(fmaxf(1e-10f, acc));
             Sout[mel_band_of(q, lane)] = db;
             vmax = fmaxf(vmax, db);
         }
