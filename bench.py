@@ -324,6 +324,32 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def run_single_pair(args):
+    """BASELINE config 1 (the reference's own CPU-runnable case): latency of ONE 3-minute pair through the drop-in
+    `pipeline.run_arrays` (host arrays in, AnalysisResult out) beside the CPU port on one core.  Not the contract line."""
+    import torch
+    from nightcore_analyzer import pipeline as npipe
+    from oracle import pipeline_port
+    nc, src = make_pairs(1, args.pair_sec)[0]
+    for _ in range(2):
+        res = npipe.run_arrays(nc, src, SR, log=None)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = npipe.run_arrays(nc, src, SR, log=None)
+    torch.cuda.synchronize()
+    gpu_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+    t0 = time.perf_counter()
+    want = pipeline_port.run_arrays(nc, src, SR, log=None)
+    cpu_s = time.perf_counter() - t0
+    same = (res.tempo_ratio, res.tempo_ci) == want["tempo"] and (res.ibi_ratio, res.ibi_ci) == want["ibi"] and \
+        res.nc_pitches_raw == want["nc_hz"]
+    print(json.dumps({"metric": "single_pair_latency_ms", "value": gpu_ms, "unit": "ms", "config": {
+        "workload": "config 1: single synthetic 3-min pair, full pipeline through pipeline.run_arrays", "pair_sec": args.pair_sec},
+        "cpu_port_seconds_1core": cpu_s, "speedup_vs_1core": cpu_s * 1e3 / gpu_ms, "identical_to_cpu_port": bool(same),
+        "tempo_ratio": res.tempo_ratio, "ibi_ratio": res.ibi_ratio, "classification": res.classification}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -339,7 +365,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-dur", type=float, default=30.0, help="source seconds per CPU-baseline pair")
     ap.add_argument("--cpu-procs", type=int, default=0)
+    ap.add_argument("--single-pair", action="store_true", help="config 1: latency of one pair through pipeline.run_arrays")
     args = ap.parse_args()
+    if args.single_pair:
+        return run_single_pair(args)
     if args.impl == "reference":
         run_reference(args)
     else:

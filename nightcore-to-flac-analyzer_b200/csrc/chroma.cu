@@ -347,14 +347,23 @@ __global__ void __launch_bounds__(kTunThreads, 1) tuning_peaks_kernel(const floa
                     const float b = __fmul_rn(__fsub_rn(sr_, sl), 0.5f);
                     const float shift = (fabsf(b) >= fabsf(a)) ? 0.0f : __fdiv_rn(-b, a);
                     mag = __fadd_rn(sc, __fmul_rn(__fmul_rn(0.5f, b), shift));
-                    const double pitch = __dmul_rn(__dadd_rn((double)k, (double)shift), hz_per_bin);
-                    double res = fmod(__dmul_rn(36.0, log2(pitch / 27.5)), 1.0);
-                    if (res >= 0.5) res = __dadd_rn(res, -1.0);
-                    int i0 = (int)floor((res + 0.5) * 100.0);
-                    i0 = i0 < 0 ? 0 : (i0 > 99 ? 99 : i0);
-                    // bin i holds edge(i) <= x < edge(i+1), edge(i) = i·0.01 − 0.5 as np.linspace computes it
-                    while (i0 > 0 && res < __dadd_rn(__dmul_rn((double)i0, 0.01), -0.5)) --i0;
-                    while (i0 < 99 && res >= __dadd_rn(__dmul_rn((double)(i0 + 1), 0.01), -0.5)) ++i0;
+                    // residual of 36·log2(f/27.5) mod 1 → one of 100 histogram bins.  Fast path in float32 (position error
+                    // < 4e-3 of a bin); anything within 2 % of a bin edge takes the exact float64 path below.
+                    const float r32 = 36.0f * __log2f(((float)k + shift) * (float)(hz_per_bin / 27.5));
+                    const float fr = r32 - floorf(r32);
+                    const float pos = (fr < 0.5f ? fr + 0.5f : fr - 0.5f) * 100.0f;
+                    int i0 = (int)pos;
+                    const float dpos = pos - (float)i0;
+                    if (!(dpos > 0.02f && dpos < 0.98f && i0 >= 0 && i0 <= 99)) {
+                        const double pitch = __dmul_rn(__dadd_rn((double)k, (double)shift), hz_per_bin);
+                        double res = fmod(__dmul_rn(36.0, log2(pitch / 27.5)), 1.0);
+                        if (res >= 0.5) res = __dadd_rn(res, -1.0);
+                        i0 = (int)floor((res + 0.5) * 100.0);
+                        i0 = i0 < 0 ? 0 : (i0 > 99 ? 99 : i0);
+                        // bin i holds edge(i) <= x < edge(i+1), edge(i) = i·0.01 − 0.5 as np.linspace computes it
+                        while (i0 > 0 && res < __dadd_rn(__dmul_rn((double)i0, 0.01), -0.5)) --i0;
+                        while (i0 < 99 && res >= __dadd_rn(__dmul_rn((double)(i0 + 1), 0.01), -0.5)) ++i0;
+                    }
                     hbin = i0;
                 }
             }
@@ -667,9 +676,9 @@ __global__ void __launch_bounds__(kCqtThreads) cqt_chroma_kernel(const float *__
 // Same contraction on the 5th-generation tensor cores:  D[128 frames × 80] (+)= A[128 × 8]·B[80 × 8]^T, kind::tf32,
 // with the TF32 split  x = hi + lo  (hi = rna_tf32(x), lo = x − hi exactly).  The hi and lo images of B are stacked
 // along N (one 160-row K-major tile [Bh; Bl]), so ONE MMA with N = 160 yields A·Bh in columns 0..79 and A·Bl in
-// columns 80..159; issuing it for A = Ah and A = Al accumulates all four partial products with 2 instructions per
-// K = 8 step (small-N tf32 MMAs are issue bound: 3 × N=80 instructions per step ran the tensor pipe at 25 %), and
-// the epilogue adds the two column halves.
+// columns 80..159; a second MMA with N = 80 adds Al·Bh into columns 0..79 (the three products of 3×TF32 with two
+// instructions per K = 8 step; Al·Bl ~ 2^-22 is dropped).  Measured cost of one tcgen05.mma kind::tf32 with M = 128 is
+// ≈ 78 + N cycles, so few wide instructions beat many narrow ones; the epilogue adds the two column halves.
 //   A (the Hankel matrix of frames) is never materialised in memory: frame thread f keeps row f, reads its 32 samples of
 //     the k-tile straight from global memory (L1/L2 serve the overlap between frames), splits them in registers and
 //     writes hi / lo into TENSOR MEMORY with tcgen05.st; the MMA reads A from TMEM (TS form).
@@ -918,7 +927,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
         }
     } else if (warp == kTcFrameWarps) {
         // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
-        constexpr uint32_t idesc = idesc_tf32(kTcFrames, kTcAccN);
+        constexpr uint32_t idesc = idesc_tf32(kTcFrames, kTcAccN);   // Ah · [Bh; Bl]  → columns 0..159
+        constexpr uint32_t idesc_lo = idesc_tf32(kTcFrames, kTcN);   // Al · Bh        → columns 0..79 (Al·Bl ~ 2^-22: dropped)
         for (int o = 0; o < kOctaves; ++o) {
             const int buf = o & 1;
             mbar_wait(&sm.acc_empty[buf], (uint32_t)(((o >> 1) & 1) ^ 1));
@@ -937,7 +947,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
                     for (int k = 0; k < kTcKT / 8; ++k) {
                         const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 32 bytes per K = 8 step inside the swizzle row
                         mma_tf32_ts(d, ah + 8 * k, bd + adv, idesc, (kt | k) != 0);
-                        mma_tf32_ts(d, al + 8 * k, bd + adv, idesc, 1);
+                        mma_tf32_ts(d, al + 8 * k, bd + adv, idesc_lo, 1);
                     }
                     commit(&sm.empty_a[sa]);
                     commit(&sm.empty_b[sb]);
