@@ -674,11 +674,10 @@ __global__ void __launch_bounds__(kCqtThreads) cqt_chroma_kernel(const float *__
 
 // ------------------------------------------------------------------------------------------------ CQT on tcgen05
 // Same contraction on the 5th-generation tensor cores:  D[128 frames × 80] (+)= A[128 × 8]·B[80 × 8]^T, kind::tf32,
-// with the TF32 split  x = hi + lo  (hi = rna_tf32(x), lo = x − hi exactly).  The hi and lo images of B are stacked
-// along N (one 160-row K-major tile [Bh; Bl]), so ONE MMA with N = 160 yields A·Bh in columns 0..79 and A·Bl in
-// columns 80..159; a second MMA with N = 80 adds Al·Bh into columns 0..79 (the three products of 3×TF32 with two
-// instructions per K = 8 step; Al·Bl ~ 2^-22 is dropped).  Measured cost of one tcgen05.mma kind::tf32 with M = 128 is
-// ≈ 78 + N cycles, so few wide instructions beat many narrow ones; the epilogue adds the two column halves.
+// with the 3×TF32 split  x = hi + lo  (hi = rna_tf32(x), lo = x − hi exactly):  A·B ≈ Ah·Bh + Al·Bh + Ah·Bl.
+// Timing experiments (NCFA_TC_DEBUG) showed the MMAs are almost free next to the producer ↔ issuer handshake, whose
+// cost is set by how many A stages are in flight — so tensor memory goes to a 5-deep A ring (320 columns) and two
+// narrow accumulators (2 × 80), rather than to wide N-stacked accumulators.
 //   A (the Hankel matrix of frames) is never materialised in memory: frame thread f keeps row f, reads its 32 samples of
 //     the k-tile straight from global memory (L1/L2 serve the overlap between frames), splits them in registers and
 //     writes hi / lo into TENSOR MEMORY with tcgen05.st; the MMA reads A from TMEM (TS form).
@@ -688,17 +687,19 @@ __global__ void __launch_bounds__(kCqtThreads) cqt_chroma_kernel(const float *__
 //     octave o−1 overlaps the MMAs of octave o.
 // Warp roles (576 threads): warps 0-15 frame warps (A producer + epilogue; warp w serves rows 32·(w & 3) … +31 — its
 // TMEM lane quarter — and column quarter q = w >> 2 of every k-tile, so four warps per scheduler hide each other's
-// latencies), warp 16 MMA issuer and TMEM allocator, warp 17 B loader.  Pipelines: A ring (3 stages in TMEM, fed through
+// latencies), warp 16 MMA issuer and TMEM allocator, warp 17 B loader.  Pipelines: A ring (5 stages in TMEM, fed through
 // a 4-deep cp.async ring in shared memory), B ring (6 stages in shared memory), accumulator ring (2).
 constexpr int kTcFrames = 128;
-constexpr int kTcFrameWarps = 16;
+constexpr int kTcQ = 2;                                  // column splits of a k-tile row (threads per frame row)
+constexpr int kTcVals = kTcKT / kTcQ;                    // samples per thread per k-tile (16)
+constexpr int kTcFrameWarps = 4 * kTcQ;
 constexpr int kTcThreads = (kTcFrameWarps + 2) * 32;     // 576
-constexpr int kTcAStages = 3;
-constexpr int kTcBStages = 6;
+constexpr int kTcAStages = 5;
+constexpr int kTcBStages = kTcAStages;                   // A and B share the stage index and ONE release barrier per stage
 constexpr int kTcACols = 2 * kTcKT;                      // hi + lo columns of one A stage
-constexpr int kTcAccCol0 = kTcAStages * kTcACols;        // 192
-constexpr int kTcAccN = 2 * kTcN;                        // accumulator columns: [A·Bh | A·Bl]
-constexpr int kTcTmemCols = 512;                         // 192 (A ring) + 2 × 160 (accumulators)
+constexpr int kTcAccCol0 = kTcAStages * kTcACols;        // 320
+constexpr int kTcAccN = kTcN;                            // accumulator columns (80: 36 real, 36 imaginary, 8 pad)
+constexpr int kTcTmemCols = 512;                         // 320 (A ring) + 2 × 80 (accumulators)
 constexpr int kTcAPre = 4;                               // k-tiles of A rows in flight (cp.async ring in shared memory)
 
 struct TcSmem {
@@ -719,8 +720,8 @@ __device__ __forceinline__ void tc_load_row8(const float *__restrict__ y, int64_
     }
 }
 
-// Epilogue share of column quarter Q: CQT bins b = 9Q … 9Q+8 of this thread's frame.  Accumulator columns: b and 36+b
-// (real / imaginary part of A·Bh), 80+b and 116+b (the same for A·Bl).  Bin b feeds chroma ((b + 1) mod 36) / 3, i.e.
+// Epilogue share of column quarter Q: CQT bins b = 9Q … 9Q+8 of this thread's frame.  Accumulator columns: b (real part)
+// and 36+b (imaginary part).  Bin b feeds chroma ((b + 1) mod 36) / 3, i.e.
 // acc[j] collects chroma (3Q + j) mod 12, j = 0..3.
 template <int Q>
 __device__ __forceinline__ void tc_epilogue_quarter(uint32_t acc_addr, float (&part)[4]) {
@@ -730,8 +731,8 @@ __device__ __forceinline__ void tc_epilogue_quarter(uint32_t acc_addr, float (&p
     for (int i = 0; i < 9; ++i) re[i] = im[i] = 0.0f;
     uint32_t v[16];
 #pragma unroll
-    for (int piece = 0; piece < 4; ++piece) {
-        constexpr int kBase[4] = {0, kCqtBins, kTcN, kTcN + kCqtBins};
+    for (int piece = 0; piece < 2; ++piece) {
+        constexpr int kBase[2] = {0, kCqtBins};
         const int c0 = kBase[piece] + 9 * Q;
         const int start = c0 & ~7;  // 8-column aligned 16-column load covers c0 … c0+8
         tmem_ld16(acc_addr + (uint32_t)start, v);
@@ -757,7 +758,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
                                                                const float *__restrict__ pyr, PyrOffsets po,
                                                                const int32_t *__restrict__ tuning_idx,
                                                                const float *__restrict__ Bimg, int tile_stride,
-                                                               double *__restrict__ partial) {
+                                                               double *__restrict__ partial, int dbg) {
     using namespace tc05;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     TcSmem &sm = *reinterpret_cast<TcSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -799,22 +800,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
 
     if (warp < kTcFrameWarps) {
         // ===================== frame warps: A producer + epilogue =====================
-        const int rg = warp & 3, q = warp >> 2;
+        const int rg = warp & 3, q = warp >> 2;   // TMEM lane quarter, column split
         const int f = 32 * rg + lane;  // row of the tile = TMEM lane
         const uint32_t lane_base = (uint32_t)(32 * rg) << 16;
         const float *pseg = pyr + (size_t)seg * po.off[kOctaves];
-        float part[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        constexpr int kQPer = 4 / kTcQ;  // epilogue quarters (9 CQT bins each) per thread
+        float part[kQPer][4];
+#pragma unroll
+        for (int a = 0; a < kQPer; ++a)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) part[a][j] = 0.0f;
 
         auto epilogue = [&](int o) {
             const int buf = o & 1;
-            mbar_wait(&sm.acc_full[buf], (uint32_t)((o >> 1) & 1));
+            mbar_wait_warp(&sm.acc_full[buf], (uint32_t)((o >> 1) & 1), 100);
             fence_after_sync();
             const uint32_t acc = tmem + lane_base + (uint32_t)(kTcAccCol0 + buf * kTcAccN);
-            switch (q) {  // warp-uniform
-                case 0: tc_epilogue_quarter<0>(acc, part); break;
-                case 1: tc_epilogue_quarter<1>(acc, part); break;
-                case 2: tc_epilogue_quarter<2>(acc, part); break;
-                default: tc_epilogue_quarter<3>(acc, part); break;
+#pragma unroll
+            for (int a = 0; a < kQPer; ++a) {
+                switch (q * kQPer + a) {  // warp-uniform
+                    case 0: tc_epilogue_quarter<0>(acc, part[a]); break;
+                    case 1: tc_epilogue_quarter<1>(acc, part[a]); break;
+                    case 2: tc_epilogue_quarter<2>(acc, part[a]); break;
+                    default: tc_epilogue_quarter<3>(acc, part[a]); break;
+                }
             }
             fence_before_sync();
             __syncwarp();
@@ -822,33 +831,55 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
         };
 
         // A rows stream through a cp.async ring (kTcAPre k-tiles ahead, flat over octaves × k-tiles): thread (f, q) owns
-        // the two 16-byte chunks 2q, 2q+1 of row f in every k-tile.  Zero padding outside [0, len) comes from the
-        // src-size (zfill) form — row starts are multiples of 4 samples, so a chunk never straddles 0.
+        // kTcVals consecutive samples (kTcVals/4 16-byte chunks) of row f in every k-tile.  Zero padding outside [0, len)
+        // comes from the src-size (zfill) form — row starts are multiples of 4 samples, so a chunk never straddles 0.
+        // The per-tile address arithmetic is kept to a handful of 32-bit operations: this instruction stream, not the
+        // MMAs or the memory system, is what paces the kernel (NCFA_TC_DEBUG timing experiments).
+        constexpr int kChunks = kTcVals / 4;
         const float *y0 = audio + seg_off[seg];
         const bool y0_aligned = (reinterpret_cast<uintptr_t>(y0) & 15u) == 0;
+        const float *yrow = nullptr;  // this thread's row start + its column offset, for the octave being issued
+        int neg_lim = 0, lim = 0;     // valid sample offsets p of the row satisfy neg_lim <= p < lim
+        bool oct_async = true;
         auto issue = [&](int it) {
-            const int o = it >> 5, kt = ((it & 31) + kshift) & 31;
-            const int hop = 512 >> o;
-            const float *y = (o == 0) ? y0 : pseg + po.off[o];
-            const int len = level_len(n, o);
-            const int64_t base = (int64_t)(t0 + f) * hop - kCqtNfft / 2 + (int64_t)kt * kTcKT + 8 * q;
-            float4 *slot = &sm.arow[it % kTcAPre][2 * q][f];
-            if (o > 0 || y0_aligned) {
+            const int kt = ((it & 31) + kshift) & 31;
+            if ((it & 31) == 0) {  // new octave: row geometry
+                const int o = it >> 5;
+                const int hop = 512 >> o;
+                const float *y = (o == 0) ? y0 : pseg + po.off[o];
+                const int len = level_len(n, o);
+                const int64_t row = (int64_t)(t0 + f) * hop - kCqtNfft / 2 + kTcVals * q;
+                yrow = y + row;
+                neg_lim = row < 0 ? (int)(-row) : 0;
+                const int64_t l64 = (int64_t)len - row;
+                lim = l64 < 0 ? 0 : (l64 > 0x3fffffff ? 0x3fffffff : (int)l64);
+                oct_async = (o > 0) || y0_aligned;
+            }
+            float4 *slot = &sm.arow[it % kTcAPre][kChunks * q][f];
+            const int p0 = kt * kTcKT;
+            if (dbg & 2) {  // timing experiment: no A traffic
+            } else if (oct_async) {
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const int64_t pos = base + 4 * c;
-                    int64_t rem = ((int64_t)len - pos) * 4;
-                    const uint32_t bytes = pos < 0 ? 0u : (uint32_t)(rem < 0 ? 0 : (rem > 16 ? 16 : rem));
-                    const float *src = bytes ? y + pos : y;
+                for (int c = 0; c < kChunks; ++c) {
+                    const int p = p0 + 4 * c;
+                    const int rem = (lim - p) * 4;
+                    const uint32_t bytes = (p < neg_lim || rem <= 0) ? 0u : (uint32_t)(rem > 16 ? 16 : rem);
+                    const float *src = bytes ? yrow + p : y0;
                     asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(slot + c * kTcFrames)),
                                  "l"(src), "r"(bytes)
                                  : "memory");
                 }
             } else {  // unaligned first level (arbitrary caller offset): plain loads into the same slot
-                float xr[8];
-                tc_load_row8(y, base, len, xr);
-                slot[0] = make_float4(xr[0], xr[1], xr[2], xr[3]);
-                slot[kTcFrames] = make_float4(xr[4], xr[5], xr[6], xr[7]);
+#pragma unroll
+                for (int c = 0; c < kChunks; ++c) {
+                    float xr[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int p = p0 + 4 * c + i;
+                        xr[i] = (p >= neg_lim && p < lim) ? __ldg(yrow + p) : 0.0f;
+                    }
+                    slot[c * kTcFrames] = make_float4(xr[0], xr[1], xr[2], xr[3]);
+                }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
@@ -860,32 +891,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
             asm volatile("cp.async.wait_group %0;" ::"n"(kTcAPre - 1) : "memory");
             const int o = it >> 5, kt = it & 31;
             const int st = it % kTcAStages;
-            uint32_t h[8], l[8];
+            uint32_t h[kTcVals], l[kTcVals];
             {
-                const float4 *slot = &sm.arow[it % kTcAPre][2 * q][f];
-                const float4 v0 = slot[0], v1 = slot[kTcFrames];
-                const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                const float4 *slot = &sm.arow[it % kTcAPre][kChunks * q][f];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float hi = to_tf32(x[i]);
-                    h[i] = __float_as_uint(hi);
-                    l[i] = __float_as_uint(x[i] - hi);
+                for (int c = 0; c < kChunks; ++c) {
+                    const float4 v = slot[c * kTcFrames];
+                    const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float hi = to_tf32(x[i]);
+                        h[4 * c + i] = __float_as_uint(hi);
+                        l[4 * c + i] = __float_as_uint(x[i] - hi);
+                    }
                 }
             }
             if (pending) {  // publish the PREVIOUS tile: its tcgen05.st had a whole iteration to land
-                wait_st();
+                if (!(dbg & 8)) wait_st();
                 fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.full_a[(it - 1) % kTcAStages]);
             }
-            mbar_wait(&sm.empty_a[st], (uint32_t)(((it / kTcAStages) & 1) ^ 1));
+            mbar_wait_warp(&sm.empty_a[st], (uint32_t)(((it / kTcAStages) & 1) ^ 1), 40);
             fence_after_sync();
-            const uint32_t a0 = tmem + lane_base + (uint32_t)(st * kTcACols + 8 * q);
-            tmem_st8(a0, h);
-            tmem_st8(a0 + kTcKT, l);
+            const uint32_t a0 = tmem + lane_base + (uint32_t)(st * kTcACols + kTcVals * q);
+            tmem_st_vals(a0, h);
+            tmem_st_vals(a0 + kTcKT, l);
             pending = true;
             if (kt == kKTiles - 1) {  // octave boundary (and the very last tile): publish before the epilogue
-                wait_st();
+                if (!(dbg & 8)) wait_st();
                 fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.full_a[st]);
@@ -898,8 +932,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
         // ---- combine the four column quarters of every frame, librosa.util.normalize(norm=inf) per frame, then the
         // tile's sum over frames (float64)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) sm.chroma_part[f][4 * q + j] = part[j];
-        asm volatile("bar.sync 1, 512;" ::: "memory");  // the sixteen frame warps only
+        for (int a = 0; a < kQPer; ++a)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sm.chroma_part[f][4 * (q * kQPer + a) + j] = part[a][j];
+        asm volatile("bar.sync 1, %0;" ::"n"(kTcFrameWarps * 32) : "memory");  // the frame warps only
         if (q == 0) {
             float chroma[kChroma];
 #pragma unroll
@@ -927,30 +963,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
         }
     } else if (warp == kTcFrameWarps) {
         // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
-        constexpr uint32_t idesc = idesc_tf32(kTcFrames, kTcAccN);   // Ah · [Bh; Bl]  → columns 0..159
-        constexpr uint32_t idesc_lo = idesc_tf32(kTcFrames, kTcN);   // Al · Bh        → columns 0..79 (Al·Bl ~ 2^-22: dropped)
+        constexpr uint32_t idesc = idesc_tf32(kTcFrames, kTcN);  // M 128 × N 80 × K 8
         for (int o = 0; o < kOctaves; ++o) {
             const int buf = o & 1;
-            mbar_wait(&sm.acc_empty[buf], (uint32_t)(((o >> 1) & 1) ^ 1));
+            mbar_wait_warp(&sm.acc_empty[buf], (uint32_t)(((o >> 1) & 1) ^ 1));
             fence_after_sync();
             const uint32_t d = tmem + (uint32_t)(kTcAccCol0 + buf * kTcAccN);
             for (int kt = 0; kt < kKTiles; ++kt) {
                 const int it = o * kKTiles + kt;
                 const int sa = it % kTcAStages, sb = it % kTcBStages;
-                mbar_wait(&sm.full_a[sa], (uint32_t)((it / kTcAStages) & 1));
-                mbar_wait(&sm.full_b[sb], (uint32_t)((it / kTcBStages) & 1));
+                mbar_wait_warp(&sm.full_a[sa], (uint32_t)((it / kTcAStages) & 1));
+                mbar_wait_warp(&sm.full_b[sb], (uint32_t)((it / kTcBStages) & 1));
                 fence_after_sync();
-                const uint64_t bd = smem_desc_k128(sm.b[sb]);  // 160 rows: Bh image then Bl image
+                const uint64_t bh = smem_desc_k128(sm.b[sb]);                  // hi image of the K tile
+                const uint64_t bl = smem_desc_k128(sm.b[sb] + kTcBTileBytes);  // lo image
                 const uint32_t ah = tmem + (uint32_t)(sa * kTcACols), al = ah + kTcKT;
                 if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < kTcKT / 8; ++k) {
                         const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 32 bytes per K = 8 step inside the swizzle row
-                        mma_tf32_ts(d, ah + 8 * k, bd + adv, idesc, (kt | k) != 0);
-                        mma_tf32_ts(d, al + 8 * k, bd + adv, idesc_lo, 1);
+                        if (dbg & 4) continue;  // timing experiment: no MMAs
+                        mma_tf32_ts(d, ah + 8 * k, bh + adv, idesc, (kt | k) != 0);  // 3×TF32: Ah·Bh + Al·Bh + Ah·Bl
+                        mma_tf32_ts(d, al + 8 * k, bh + adv, idesc, 1);
+                        mma_tf32_ts(d, ah + 8 * k, bl + adv, idesc, 1);
                     }
-                    commit(&sm.empty_a[sa]);
-                    commit(&sm.empty_b[sb]);
+                    commit(&sm.empty_a[sa]);  // frees the A stage (TMEM) and the B stage (shared memory) of this tile together:
+                                              // tcgen05.commit is the scarce operation of this pipeline, one per tile
                     if (kt == kKTiles - 1) commit(&sm.acc_full[buf]);
                 }
                 __syncwarp();
@@ -961,10 +999,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
         const unsigned char *src = reinterpret_cast<const unsigned char *>(Bimg) + (size_t)tj * kKTiles * kTcBStageBytes;
         for (int it = 0; it < kIters; ++it) {
             const int sb = it % kTcBStages, kt = ((it % kKTiles) + kshift) & (kKTiles - 1);
-            mbar_wait(&sm.empty_b[sb], (uint32_t)(((it / kTcBStages) & 1) ^ 1));
+            mbar_wait_warp(&sm.empty_a[sb], (uint32_t)(((it / kTcBStages) & 1) ^ 1), 100);
             if (elect_one()) {
-                mbar_arrive_expect_tx(&sm.full_b[sb], kTcBStageBytes);
-                bulk_g2s(sm.b[sb], src + (size_t)kt * kTcBStageBytes, kTcBStageBytes, &sm.full_b[sb]);
+                if ((dbg & 1) && it >= kTcBStages) {  // timing experiment: no B traffic after the first ring fill
+                    mbar_arrive(&sm.full_b[sb]);
+                } else {
+                    mbar_arrive_expect_tx(&sm.full_b[sb], kTcBStageBytes);
+                    bulk_g2s(sm.b[sb], src + (size_t)kt * kTcBStageBytes, kTcBStageBytes, &sm.full_b[sb]);
+                }
             }
             __syncwarp();
         }
@@ -1129,8 +1171,13 @@ extern "C" int ncfa_chroma_mean_batched(const float *d_audio, const int64_t *d_s
     if (use_tc) {
         ProfScope _p("cqt_tc_kernel", st);
         dim3 g((cqt_frames(max_seg_len) + kTcFrames - 1) / kTcFrames, n_seg);
+        static int dbg = -1;
+        if (dbg < 0) {
+            const char *e = getenv("NCFA_TC_DEBUG");  // timing experiments only (results are wrong when non-zero)
+            dbg = e ? atoi(e) : 0;
+        }
         cqt_tc_kernel<<<g, kTcThreads, sizeof(TcSmem) + 1024, st>>>(d_audio, d_seg_off, d_seg_len, pyr, po, d_tuning_idx,
-                                                                    ct.Bimg, tiles, partial);
+                                                                    ct.Bimg, tiles, partial, dbg);
         NCFA_LAUNCH_OK("cqt_tc_kernel");
     } else {
         ProfScope _p("cqt_chroma_kernel", st);
