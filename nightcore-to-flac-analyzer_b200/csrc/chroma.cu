@@ -288,7 +288,7 @@ __host__ __device__ inline void pyramid_layout(int max_len, size_t off[kOctaves 
 }
 
 // ------------------------------------------------------------------------------------------------ tuning
-constexpr int kTunWarps = 16;
+constexpr int kTunWarps = 20;
 constexpr int kTunThreads = kTunWarps * 32;
 
 struct TuningSmem {

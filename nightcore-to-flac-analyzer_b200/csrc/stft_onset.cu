@@ -17,7 +17,7 @@
 
 namespace ncfa {
 
-constexpr int kWarps = 16;
+constexpr int kWarps = 20;
 constexpr int kThreads = kWarps * 32;
 constexpr int kMelRowsMax = 128;
 
