@@ -74,13 +74,19 @@ def pin_pairs(pairs: Sequence[Tuple[np.ndarray, np.ndarray]], sr: int = SAMPLE_R
     return PinnedBatch(pinned=pinned, off=off, length=length, sr=sr)
 
 
-def upload(pb: PinnedBatch, n_pairs: Optional[int] = None) -> StagedBatch:
-    """One asynchronous H2D copy of the first ``n_pairs`` pairs of a pinned batch."""
+def upload(pb: PinnedBatch, n_pairs: Optional[int] = None, out: Optional[torch.Tensor] = None) -> StagedBatch:
+    """One asynchronous H2D copy of the first ``n_pairs`` pairs of a pinned batch (into ``out`` when given: a
+    preallocated device buffer avoids allocator traffic — and its implicit synchronisations — in a streaming loop)."""
     eng = _engine.get_engine()
     k = pb.n_pairs if n_pairs is None else min(int(n_pairs), pb.n_pairs)
     off, length = pb.off[: 2 * k], pb.length[: 2 * k]
     total = int(off[-1] + (length[-1] + 3) // 4 * 4) if k else 0
-    audio = pb.pinned[: max(total, 4)].to(eng.device, non_blocking=True)
+    n = max(total, 4)
+    if out is not None and out.numel() >= n:
+        audio = out[:n]
+        audio.copy_(pb.pinned[:n], non_blocking=True)
+    else:
+        audio = pb.pinned[:n].to(eng.device, non_blocking=True)
     eng.h2d_bytes += 4 * total
     return StagedBatch(audio=audio, off=off.copy(), length=length.copy(), sr=pb.sr, h2d_bytes=4 * total)
 
@@ -325,11 +331,13 @@ def run_subbatches(jobs: Sequence, fn, workers: int = 2, prepare=None) -> list:
                 return jobs[i], None
             copies[w].wait_stream(streams[w])      # the allocator may hand out a block last used by this worker's kernels
             with torch.cuda.stream(copies[w]):
-                x = prepare(jobs[i])
+                x = prepare(jobs[i], w, stage.count)
+                stage.count += 1
                 ev = torch.cuda.Event()
                 ev.record(copies[w])
             return x, ev
 
+        stage.count = 0
         nxt = stage(mine[0]) if mine else None
         with torch.cuda.stream(streams[w]):
             for n, i in enumerate(mine):
@@ -363,8 +371,21 @@ def analyse_pinned(pb: PinnedBatch, sizes: Sequence[int], stats: Optional[dict] 
         s1["h2d_bytes"] = st.h2d_bytes
         return res, s1
 
+    # two preallocated device buffers per worker: slot n is reused for the worker's job n+2, which is uploaded while
+    # job n+1 runs, i.e. after job n has delivered its results
+    eng = _engine.get_engine()
+    kmax = max(sizes) if sizes else 0
+    need = int(pb.off[2 * kmax - 1] + (pb.length[2 * kmax - 1] + 3) // 4 * 4) if kmax else 4
+    nw = max(1, min(workers, len(sizes)))
+    key = (eng.device.index, nw, need)
+    if _UPLOAD_BUFFERS.get("key") != key:
+        _UPLOAD_BUFFERS.clear()
+        _UPLOAD_BUFFERS["key"] = key
+        _UPLOAD_BUFFERS["buf"] = [[torch.empty(max(need, 4), dtype=torch.float32, device=eng.device) for _ in range(2)]
+                                  for _ in range(nw)]
+    bufs = _UPLOAD_BUFFERS["buf"]
     results: list = []
-    for res, s1 in run_subbatches(list(sizes), one, workers, prepare=lambda k: upload(pb, k)):
+    for res, s1 in run_subbatches(list(sizes), one, workers, prepare=lambda k, w, n: upload(pb, k, out=bufs[w][n % 2])):
         results += res
         if stats is not None:
             for key, v in s1.items():
@@ -388,6 +409,7 @@ def analyse_resident(batches: Sequence[StagedBatch], stats: Optional[dict] = Non
 
 
 _WORKER_STREAMS: dict = {}
+_UPLOAD_BUFFERS: dict = {}
 
 
 def _worker_stream(device, w: int) -> "torch.cuda.Stream":
