@@ -80,8 +80,14 @@ __device__ double select_localmax(const double *cum, int n, int rank, int *hist,
 __global__ void beat_track_kernel(const float *__restrict__ onset, const int64_t *__restrict__ onset_off,
                                   const int32_t *__restrict__ env_len, int env_stride, const int32_t *__restrict__ lag,
                                   double *__restrict__ ws_f64, int32_t *__restrict__ ws_i32, int max_fpb,
-                                  int32_t *__restrict__ beats_out, int max_beats, int32_t *__restrict__ n_beats) {
-    extern __shared__ double sh_d[];  // blockDim doubles
+                                  int32_t *__restrict__ beats_out, int max_beats, int32_t *__restrict__ n_beats,
+                                  int ring) {
+    // blockDim doubles (reductions) | ring doubles: cumulative scores of the last `ring` frames (power of two >=
+    // far + near for every admissible fpb) | transition penalties for d = near .. far
+    extern __shared__ double sh_d[];
+    double *cring = sh_d + blockDim.x;
+    double *pen = cring + ring;
+    const int rmask = ring - 1;
     __shared__ int hist[256];
     __shared__ unsigned long long s_prefix;
     __shared__ int s_rank, s_cnt, s_n0, s_n1;
@@ -99,7 +105,7 @@ __global__ void beat_track_kernel(const float *__restrict__ onset, const int64_t
     const size_t K = 2 * (size_t)max_fpb + 1;
     double *base = ws_f64 + (size_t)seg * (3 * (size_t)env_stride + 2 * K + 8);
     double *onorm = base, *ls = base + env_stride, *cum = base + 2 * (size_t)env_stride;
-    double *window = base + 3 * (size_t)env_stride, *pen = window + K;
+    double *window = base + 3 * (size_t)env_stride;
     int32_t *backlink = ws_i32 + (size_t)seg * 2 * env_stride, *tmp = backlink + env_stride;
 
     // ---- onsets / (std(ddof=1) + tiny)
@@ -175,8 +181,9 @@ __global__ void beat_track_kernel(const float *__restrict__ onset, const int64_t
             if (active) {
                 int lo = i - far;
                 if (lo < 0) lo = 0;
+#pragma unroll 4
                 for (int loc = i - near - sub; loc >= lo; loc -= L) {
-                    const double sc = cum[loc] - pen[i - loc - near];
+                    const double sc = cring[loc & rmask] - pen[i - loc - near];
                     if (sc > best) {
                         best = sc;
                         bl = loc;
@@ -192,7 +199,9 @@ __global__ void beat_track_kernel(const float *__restrict__ onset, const int64_t
                 }
             }
             if (active && sub == 0) {
-                cum[i] = (bl >= 0) ? ls[i] + best : ls[i];
+                const double c = (bl >= 0) ? ls[i] + best : ls[i];
+                cum[i] = c;
+                cring[i & rmask] = c;  // frames of this wavefront never alias the ones being read: ring >= far + near
                 backlink[i] = (i < first) ? -1 : bl;
             }
         }
@@ -269,6 +278,13 @@ __global__ void beat_track_kernel(const float *__restrict__ onset, const int64_t
     }
 }
 
+// shared-memory ring for the DP: power of two >= far + near = 2·fpb + round(fpb/2) at fpb = max_fpb
+static int beat_ring(int max_fpb) {
+    int r = 64;
+    while (r < 2 * max_fpb + max_fpb / 2 + 2) r *= 2;
+    return r;
+}
+
 static size_t beat_f64_per_seg(int max_env_len, int max_fpb) {
     return 3 * (size_t)max_env_len + 2 * (2 * (size_t)max_fpb + 1) + 8;
 }
@@ -298,11 +314,16 @@ extern "C" int ncfa_beat_track_batched(const float *d_onset, const int64_t *d_on
     double *wf = (double *)d_workspace;
     int32_t *wi = (int32_t *)((char *)d_workspace +
                               align_up((size_t)n_seg * beat_f64_per_seg(max_env_len, max_lag) * 8, 256));
-    const int threads = max_env_len <= 2048 ? 64 : 512;
+    const int threads = max_env_len <= 2048 ? 64 : 1024;
+    const int ring = beat_ring(max_lag);
+    const size_t smem = ((size_t)threads + ring + (3 * (size_t)max_lag / 2 + 4)) * sizeof(double);
+    int rc = ensure_dynamic_smem((const void *)beat_track_kernel, smem);
+    if (rc) return rc;
     {
-        ProfScope _p("beat_track_kernel", (cudaStream_t)stream);
-        beat_track_kernel<<<n_seg, threads, threads * sizeof(double), (cudaStream_t)stream>>>(
-        d_onset, d_onset_off, d_env_len, max_env_len, d_lag, wf, wi, max_lag, d_beats, max_beats, d_n_beats);
+        ProfScope _p(max_env_len <= 2048 ? "beat_track_kernel" : "beat_track_kernel[long]", (cudaStream_t)stream);
+        beat_track_kernel<<<n_seg, threads, smem, (cudaStream_t)stream>>>(d_onset, d_onset_off, d_env_len, max_env_len,
+                                                                       d_lag, wf, wi, max_lag, d_beats, max_beats,
+                                                                       d_n_beats, ring);
     }
     NCFA_LAUNCH_OK("beat_track_kernel");
     return NCFA_OK;

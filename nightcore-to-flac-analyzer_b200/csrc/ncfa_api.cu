@@ -183,6 +183,42 @@ int get_tables(int sr, Tables *out) {
         if ((rc = upload(wt, &dt.t.mel_wt))) return rc;
         if ((rc = upload(lb, &dt.t.mel_lane_bin0))) return rc;
     }
+    // band-major float4 copy + the split of the bands over the 16 warps of the tile kernel
+    {
+        std::vector<float4> w4;
+        std::vector<int> start4(n_mels + 1);
+        for (int m = 0; m < n_mels; ++m) {
+            start4[m] = (int)w4.size();
+            for (int i = start[m]; i < start[m + 1]; i += 4) {
+                float q[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int j = 0; j < 4 && i + j < start[m + 1]; ++j) q[j] = w[i + j];
+                w4.push_back(make_float4(q[0], q[1], q[2], q[3]));
+            }
+            if (bin0[m] + 4 * ((int)w4.size() - start4[m]) > 1028) {
+                set_error("mel band %d reaches past the padded power tile at sr=%d", m, sr);
+                return NCFA_E_OVERFLOW;
+            }
+        }
+        start4[n_mels] = (int)w4.size();
+        if (w4.empty()) w4.push_back(make_float4(0.f, 0.f, 0.f, 0.f));
+        // cost of a band in the mel phase ~ 4 per float4 group + a fixed epilogue; contiguous split into 16 parts
+        auto cost = [&](int m) { return 4 * (start4[m + 1] - start4[m]) + 8; };
+        long total = 0;
+        for (int m = 0; m < n_mels; ++m) total += cost(m);
+        int m = 0;
+        long acc = 0;
+        for (int wp = 0; wp < 16; ++wp) {
+            dt.t.mel_warp_band[wp] = m;
+            const long target = total * (wp + 1) / 16;
+            while (m < n_mels && acc + cost(m) / 2 <= target) {
+                acc += cost(m);
+                ++m;
+            }
+        }
+        dt.t.mel_warp_band[16] = n_mels;
+        if ((rc = upload(w4, &dt.t.mel_w4))) return rc;
+        if ((rc = upload(start4, &dt.t.mel_start4))) return rc;
+    }
     if ((rc = upload(hann, &dt.t.hann))) return rc;
     if ((rc = upload(tw1024, &dt.t.tw1024))) return rc;
     if ((rc = upload(tw2048, &dt.t.tw2048))) return rc;

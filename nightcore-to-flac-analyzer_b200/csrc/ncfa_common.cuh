@@ -79,6 +79,12 @@ struct Tables {
     const float *mel_wt;
     const int *mel_lane_bin0;  // [4][32] first FFT bin of the band of (q, lane)
     int mel_qoff[4], mel_qw[4], mel_wt_rows;
+    // band-major bank for the tile kernel (stft_onset.cu): band m = float4 groups [mel_start4[m], mel_start4[m+1]) of
+    // mel_w4, first weight at bin mel_bin0[m], zero padded to a multiple of four; warp w of the 16 owns the bands
+    // [mel_warp_band[w], mel_warp_band[w+1]) (balanced by weight count)
+    const float4 *mel_w4;
+    const int *mel_start4;    // [129]
+    int mel_warp_band[17];
 };
 __host__ __device__ inline int mel_band_of(int q, int lane) {
     return q == 0 ? lane : (q == 1 ? 63 - lane : (q == 2 ? 64 + lane : 127 - lane));

@@ -13,6 +13,7 @@
 // un-packs the real spectrum with one shuffle per complex value.  The power spectrum goes through the
 // same per-warp tile into the sparse mel projection (lane owns bands l, 63−l, 64+l, 127−l; weights are
 // stored lane-transposed so the reads are bank-conflict free).  No block-level synchronisation in the loop.
+#include <stdlib.h>
 #include "stft_core.cuh"
 
 namespace ncfa {
@@ -111,13 +112,150 @@ __global__ void __launch_bounds__(256) flux_kernel(const float *__restrict__ S, 
     if (lane == 0) out[j] = s * (1.0f / NCFA_N_MELS);
 }
 
+// ---- tile form (cross-check) ------------------------------------------------------------------------------------------
+// The warp-per-frame kernel above spends more shared-memory wavefronts in the mel projection (lane-dependent, bank
+// conflicting reads of the power spectrum) than in the FFT.  Here a CTA of 16 warps works on a TILE of 32 consecutive
+// frames of one segment in two phases:
+//   1. FFT phase: warp w transforms frames w and w+16 of the tile; the power spectrum of frame f becomes column f of
+//      a shared [1028 bins][33] tile (same arithmetic as above; transposes go through a 4.2 KB per-warp float tile,
+//      real then imaginary parts, to make room);
+//   2. mel phase: lane = frame, warp w owns a contiguous group of mel bands (balanced by weight count); the weights
+//      are warp-uniform float4 loads, the power reads are conflict free — 1 shared wavefront + 1 FFMA per
+//      (band, bin) pair for 32 frames at once, i.e. 63 of each per frame instead of ~360 wavefronts.
+// The log-mel scratch is tile-major, S[tile][band][32 frames] (coalesced stores here, coalesced loads in the flux
+// kernel).  Sums run in the same order as in the warp form, so both produce the same onset envelope bit for bit.
+constexpr int kTileWarps = 16;
+constexpr int kTileThreads = kTileWarps * 32;
+constexpr int kTileFrames = 32;
+
+struct TileSmem {
+    float hann[2048];
+    float2 tw[1024];
+    float scr[kTileWarps][32 * kScrStride];
+    float P[kPRows * kPStride];
+};
+
+__global__ void __launch_bounds__(kTileThreads, 1) stft_logmel_tile_kernel(const float *__restrict__ audio,
+                                                                           const int64_t *__restrict__ seg_off,
+                                                                           const int32_t *__restrict__ seg_len,
+                                                                           int n_seg, int hop, int tiles_per_seg,
+                                                                           Tables tb, float *__restrict__ S,
+                                                                           unsigned *__restrict__ seg_max) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TileSmem &sm = *reinterpret_cast<TileSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 2048; i += kTileThreads) sm.hann[i] = tb.hann[i];
+    for (int i = tid; i < 1024; i += kTileThreads) sm.tw[i] = tb.tw1024[i];
+    for (int i = tid; i < kPRows * kPStride; i += kTileThreads) sm.P[i] = 0.0f;  // padding rows must stay finite
+    __syncthreads();
+
+    const cf twl = cf{tb.tw2048[lane].x, tb.tw2048[lane].y};
+    const int mb0 = tb.mel_warp_band[warp], mb1 = tb.mel_warp_band[warp + 1];
+    const int total = n_seg * tiles_per_seg;
+    int cur_seg = -1;
+    float cur_max = -INFINITY;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int seg = tile / tiles_per_seg;
+        const int f0 = (tile - seg * tiles_per_seg) * kTileFrames;
+        const int len = seg_len[seg];
+        const int n_frames = 1 + len / hop;
+        if (f0 >= n_frames) continue;  // CTA-uniform
+        const float *src = audio + seg_off[seg];
+#pragma unroll 1
+        for (int r = 0; r < kTileFrames / kTileWarps; ++r) {
+            const int f = warp + kTileWarps * r;
+            if (f0 + f < n_frames)
+                warp_power_spectrum_global_tile(src, (int64_t)(f0 + f) * hop - 1024, len, sm.hann, sm.tw, sm.scr[warp],
+                                                sm.P + f, twl, lane);
+        }
+        __syncthreads();
+        if (seg != cur_seg) {
+            if (cur_seg >= 0 && lane == 0) atomicMax(seg_max + cur_seg, float_to_ordered(cur_max));
+            cur_seg = seg;
+            cur_max = -INFINITY;
+        }
+        const bool valid = f0 + lane < n_frames;
+        float *Sout = S + (size_t)tile * (NCFA_N_MELS * kTileFrames) + lane;
+        float vmax = -INFINITY;
+        for (int m = mb0; m < mb1; ++m) {
+            const int g0 = __ldg(tb.mel_start4 + m), g1 = __ldg(tb.mel_start4 + m + 1);
+            const float4 *wq = tb.mel_w4 + g0;
+            const float *p = sm.P + __ldg(tb.mel_bin0 + m) * kPStride + lane;
+            float acc = 0.0f;
+            for (int g = 0; g < g1 - g0; ++g) {
+                const float4 wv = __ldg(wq + g);
+                acc = fmaf(wv.x, p[0], acc);
+                acc = fmaf(wv.y, p[kPStride], acc);
+                acc = fmaf(wv.z, p[2 * kPStride], acc);
+                acc = fmaf(wv.w, p[3 * kPStride], acc);
+                p += 4 * kPStride;
+            }
+            const float db = 10.0f * log10f(fmaxf(1e-10f, acc));
+            if (valid) {
+                Sout[m * kTileFrames] = db;
+                vmax = fmaxf(vmax, db);
+            }
+        }
+        cur_max = fmaxf(cur_max, warp_max(vmax));
+        __syncthreads();  // the next tile's FFT phase overwrites P
+    }
+    if (cur_seg >= 0 && lane == 0) atomicMax(seg_max + cur_seg, float_to_ordered(cur_max));
+}
+
+// flux over the tile-major scratch: one thread per output frame walks the 128 bands of frames j-pad and j-pad+1
+// (lanes = consecutive frames: coalesced), summing in the order of flux_kernel (4 bands per partial, xor tree).
+__global__ void __launch_bounds__(128) flux_tile_kernel(const float *__restrict__ S, const unsigned *__restrict__ seg_max,
+                                                        const int32_t *__restrict__ seg_len, int hop, int tiles_per_seg,
+                                                        int pad, float *__restrict__ onset,
+                                                        const int64_t *__restrict__ onset_off) {
+    const int seg = blockIdx.y;
+    const int n_frames = 1 + seg_len[seg] / hop;
+    const int j = blockIdx.x * 128 + threadIdx.x;
+    if (j >= n_frames) return;
+    float *out = onset + onset_off[seg];
+    if (j < pad) {
+        out[j] = 0.0f;
+        return;
+    }
+    const float floor_db = ordered_to_float(seg_max[seg]) - 80.0f;
+    const int ja = j - pad, jb = ja + 1;
+    const float *base = S + (size_t)seg * tiles_per_seg * (NCFA_N_MELS * kTileFrames);
+    const float *pa = base + (size_t)(ja >> 5) * (NCFA_N_MELS * kTileFrames) + (ja & 31);
+    const float *pb = base + (size_t)(jb >> 5) * (NCFA_N_MELS * kTileFrames) + (jb & 31);
+    float q[32];
+#pragma unroll
+    for (int l = 0; l < 32; ++l) {
+        float s = fmaxf(0.0f, fmaxf(pb[(4 * l) * kTileFrames], floor_db) - fmaxf(pa[(4 * l) * kTileFrames], floor_db));
+        s += fmaxf(0.0f, fmaxf(pb[(4 * l + 1) * kTileFrames], floor_db) - fmaxf(pa[(4 * l + 1) * kTileFrames], floor_db));
+        s += fmaxf(0.0f, fmaxf(pb[(4 * l + 2) * kTileFrames], floor_db) - fmaxf(pa[(4 * l + 2) * kTileFrames], floor_db));
+        s += fmaxf(0.0f, fmaxf(pb[(4 * l + 3) * kTileFrames], floor_db) - fmaxf(pa[(4 * l + 3) * kTileFrames], floor_db));
+        q[l] = s;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int l = 0; l < o; ++l) q[l] = q[l] + q[l + o];
+    out[j] = q[0] * (1.0f / NCFA_N_MELS);
+}
+
+// measured on B200 (profiles/r1ai): the tile form is 7 % (hop 64) to 19 % (hop 512) SLOWER than the warp form — fewer
+// resident warps, two block barriers per tile and four shared round trips per transpose cost more than the mel phase
+// saves — so the warp form stays the default and the tile form is kept as a cross-check (NCFA_STFT_IMPL=tile).
+static bool use_warp_form() {
+    static const bool v = [] {
+        const char *e = getenv("NCFA_STFT_IMPL");
+        return !(e && strcmp(e, "tile") == 0);
+    }();
+    return v;
+}
+
 }  // namespace ncfa
 
 using namespace ncfa;
 
 extern "C" size_t ncfa_onset_workspace_bytes(int n_seg, int max_seg_len, int hop) {
     if (n_seg <= 0 || hop <= 0 || max_seg_len < 0) return 0;
-    size_t frames = 1 + (size_t)max_seg_len / hop;
+    size_t frames = (1 + (size_t)max_seg_len / hop + 31) / 32 * 32;  // whole tiles of 32 frames
     return align_up((size_t)n_seg * frames * NCFA_N_MELS * sizeof(float), 256) + align_up((size_t)n_seg * 4, 256);
 }
 
@@ -140,10 +278,33 @@ extern "C" int ncfa_onset_strength_batched(const float *d_audio, const int64_t *
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int frames = 1 + max_seg_len / hop;
+    const int tiles_per_seg = (frames + kTileFrames - 1) / kTileFrames;
     float *S = (float *)d_workspace;
-    unsigned *seg_max = (unsigned *)((char *)d_workspace + align_up((size_t)n_seg * frames * NCFA_N_MELS * 4, 256));
+    unsigned *seg_max =
+        (unsigned *)((char *)d_workspace + align_up((size_t)n_seg * tiles_per_seg * kTileFrames * NCFA_N_MELS * 4, 256));
     NCFA_CUDA_OK(cudaMemsetAsync(seg_max, 0, (size_t)n_seg * 4, st));
     int n_sm = 0;
+    const int pad_t = 1 + NCFA_N_FFT / (2 * hop);
+    if (!use_warp_form()) {
+        NCFA_REQUIRE((int64_t)n_seg * tiles_per_seg < (int64_t)1 << 31, "too many frame tiles in one call");
+        if ((rc = ensure_dynamic_smem((const void *)stft_logmel_tile_kernel, sizeof(TileSmem)))) return rc;
+        if ((rc = sm_count(&n_sm))) return rc;
+        {
+            const int64_t tiles = (int64_t)n_seg * tiles_per_seg;
+            const int grid = (int)(tiles < n_sm ? tiles : n_sm);  // persistent: one CTA per SM
+            ProfScope _p(hop <= 128 ? "stft_logmel_kernel[hop<=128]" : "stft_logmel_kernel[hop>128]", st);
+            stft_logmel_tile_kernel<<<grid, kTileThreads, sizeof(TileSmem), st>>>(d_audio, d_seg_off, d_seg_len, n_seg, hop,
+                                                                                 tiles_per_seg, tb, S, seg_max);
+        }
+        NCFA_LAUNCH_OK("stft_logmel_tile_kernel");
+        dim3 g2((frames + 127) / 128, n_seg);
+        {
+            ProfScope _p("flux_kernel", st);
+            flux_tile_kernel<<<g2, 128, 0, st>>>(S, seg_max, d_seg_len, hop, tiles_per_seg, pad_t, d_onset, d_onset_off);
+        }
+        NCFA_LAUNCH_OK("flux_tile_kernel");
+        return NCFA_OK;
+    }
     if ((rc = ensure_dynamic_smem((const void *)stft_logmel_kernel, sizeof(OnsetSmem)))) return rc;
     if ((rc = sm_count(&n_sm))) return rc;
     {

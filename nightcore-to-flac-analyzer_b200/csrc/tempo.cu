@@ -21,7 +21,7 @@
 
 namespace ncfa {
 
-constexpr int kLagThreads = 256;
+constexpr int kLagThreads = 128;
 constexpr double kReinitRatio = 1e-4;  // re-sum exactly when the frame energy collapses
 
 // x[m], m in [0, n + 2p): envelope padded with np.pad(mode='linear_ramp', end_values=0)
@@ -55,7 +55,8 @@ __global__ void __launch_bounds__(kR0Threads) tg_r0_kernel(const float *__restri
                                                            const int64_t *__restrict__ onset_off,
                                                            const int32_t *__restrict__ env_len, int env_stride, int W,
                                                            const double2 *__restrict__ trig,
-                                                           const double *__restrict__ w2, double *__restrict__ r0) {
+                                                           const double *__restrict__ w2, double *__restrict__ r0,
+                                                           double *__restrict__ r0inv) {
     extern __shared__ double zs[];  // r0_pad(kR0Threads·kR0Block + W) squared padded-envelope samples
     const int seg = blockIdx.y;
     const int n = env_len[seg];
@@ -89,6 +90,7 @@ __global__ void __launch_bounds__(kR0Threads) tg_r0_kernel(const float *__restri
     }
     const double2 e1 = trig[1 % W], e2 = trig[2 % W];
     double *out = r0 + (size_t)seg * env_stride;
+    double *out_inv = r0inv + (size_t)seg * env_stride;
     for (int t = tb; t < te; ++t) {
         const int o = t - f0;
         double r = 0.375 * S0 - 0.5 * S1r + 0.125 * S2r;
@@ -97,6 +99,9 @@ __global__ void __launch_bounds__(kR0Threads) tg_r0_kernel(const float *__restri
             for (int j = 0; j < W; ++j) r = fma(__ldg(w2 + j), zs[r0_pad(o + j)], r);
         }
         out[t] = r;
+        // librosa.util.normalize(norm=inf): frames whose max (= R_t[0]) is below tiny stay unscaled.  The reciprocal is
+        // the same for every lag, so it is taken once here instead of once per (lag, frame) in tg_lag_kernel.
+        out_inv[t] = (r < 2.2250738585072014e-308) ? 1.0 : 1.0 / r;
         if (t + 1 < te) {
             const double d = zs[r0_pad(o + W)] - zs[r0_pad(o)];  // e^{iθW} = 1: the entering sample has phase 0 after the shift
             S0 += d;
@@ -109,13 +114,50 @@ __global__ void __launch_bounds__(kR0Threads) tg_r0_kernel(const float *__restri
     }
 }
 
-// pass 2: partial[seg][chunk][k] = Σ_{t in chunk} R_t[k] / R_t[0]
+// pass 1b: which frames must rebuild the running sums from scratch?  The first frame of every chunk, and every frame
+// whose energy R_t[0] collapses below kReinitRatio of the largest energy since the last rebuild (the sliding update
+// would otherwise carry the rounding error of sums 10^4 times larger).  The decision depends on the frame only, so it
+// is taken once here — one warp per (segment, chunk), lanes load 32 frames at a time and replay them in order — and
+// stored in the SIGN of r0inv (1/R_t[0] > 0): tg_lag_kernel then needs a single uniform load per frame.
+__global__ void __launch_bounds__(128) tg_flags_kernel(const int32_t *__restrict__ env_len, int env_stride, int chunk,
+                                                       int n_chunks, int n_seg, const double *__restrict__ r0,
+                                                       double *__restrict__ r0inv) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n_seg * n_chunks) return;
+    const int seg = w / n_chunks, c = w - seg * n_chunks;
+    const int n = env_len[seg];
+    const int t0 = c * chunk;
+    if (t0 >= n) return;
+    const int t1 = min(n, t0 + chunk);
+    const double *e = r0 + (size_t)seg * env_stride;
+    double *inv = r0inv + (size_t)seg * env_stride;
+    double runmax = 0.0;
+    bool first = true;
+    for (int tb = t0; tb < t1; tb += 32) {
+        const int t = tb + lane;
+        const double mine = (t < t1) ? e[t] : 0.0;
+        bool flag = false;
+        const int cnt = min(32, t1 - tb);
+        for (int l = 0; l < cnt; ++l) {
+            const double e0 = __shfl_sync(0xffffffffu, mine, l);
+            const bool f = first || (e0 < kReinitRatio * runmax);
+            if (f) runmax = e0;
+            runmax = fmax(runmax, e0);
+            first = false;
+            if (l == lane) flag = f;
+        }
+        if (t < t1 && flag) inv[t] = -inv[t];
+    }
+}
+
+// pass 2: partial[seg][chunk][k] = Σ_{t in chunk} R_t[k] / R_t[0] for the lags k in todo[seg] \ done[seg] (exact
+// intervals; CTA b covers todo.x + 128·b …, warps without a live lag leave at once).  One thread = one lag.
 __global__ void __launch_bounds__(kLagThreads) tg_lag_kernel(const float *__restrict__ onset,
                                                              const int64_t *__restrict__ onset_off,
                                                              const int32_t *__restrict__ env_len, int env_stride,
-                                                             int W, int chunk, int n_chunks, int k_min,
+                                                             int W, int chunk, int n_chunks,
                                                              const double2 *__restrict__ trig,
-                                                             const double *__restrict__ r0,
+                                                             const double *__restrict__ r0inv,
                                                              const int2 *__restrict__ todo,
                                                              const int2 *__restrict__ done,
                                                              double *__restrict__ partial) {
@@ -124,15 +166,13 @@ __global__ void __launch_bounds__(kLagThreads) tg_lag_kernel(const float *__rest
     const int n = env_len[seg];
     const int t0 = blockIdx.y * chunk;
     if (t0 >= n) return;
-    {
-        // lag block [kb, ke): evaluate iff it intersects todo[seg] and is not inside done[seg] (both block aligned)
-        const int kb = k_min + blockIdx.x * kLagThreads, ke = kb + kLagThreads;
-        const int2 td = todo[seg];
-        if (ke <= td.x || kb >= td.y) return;
-        if (done != nullptr) {
-            const int2 dn = done[seg];
-            if (kb >= dn.x && kb < dn.y) return;
-        }
+    const int2 td = todo[seg];
+    const int kb = td.x + blockIdx.x * kLagThreads;
+    if (kb >= td.y || kb >= W) return;
+    int2 dn = make_int2(0, 0);
+    if (done != nullptr) {
+        dn = done[seg];
+        if (kb >= dn.x && min(kb + kLagThreads, td.y) <= dn.y) return;
     }
     const int t1 = min(n, t0 + chunk);
     const float *on = onset + onset_off[seg];
@@ -143,8 +183,9 @@ __global__ void __launch_bounds__(kLagThreads) tg_lag_kernel(const float *__rest
         xs[i] = (m < n + 2 * p) ? padded_env(on, n, p, m) : 0.0;
     }
     __syncthreads();
-    const int k = k_min + blockIdx.x * kLagThreads + threadIdx.x;
-    const bool active = k < W;
+    const int k = kb + threadIdx.x;
+    const bool active = k < td.y && k < W && !(k >= dn.x && k < dn.y);
+    if (!__any_sync(0xffffffffu, active)) return;
     const int kk = active ? k : W - 1;
     const int L = W - kk;
     const double2 ek = trig[kk];
@@ -152,42 +193,44 @@ __global__ void __launch_bounds__(kLagThreads) tg_lag_kernel(const float *__rest
     const double2 eL = trig[L % W], e2L = trig[(2 * L) % W];
     const double q0 = 0.25 * (1.0 + 0.5 * ek.x), q1r = -0.25 * (1.0 + ek.x), q1i = 0.25 * ek.y,
                  q2r = 0.125 * ek.x, q2i = -0.125 * ek.y;
-    const double *r0s = r0 + (size_t)seg * env_stride;
-    // the warp's longest window (smallest k) bounds the uniform init loop
-    const int Lmax = W - (k_min + blockIdx.x * kLagThreads + (threadIdx.x & ~31));
-    double S0 = 0, S1r = 0, S1i = 0, S2r = 0, S2i = 0, acc = 0, runmax = 0;
-    bool need_init = true;
-    for (int t = t0; t < t1; ++t) {
-        const double e0 = r0s[t];
-        const int o = t - t0;
-        if (e0 < kReinitRatio * runmax) need_init = true;  // warp-uniform: depends on t only
-        if (need_init) {
-            S0 = S1r = S1i = S2r = S2i = 0;
-            for (int j = 0; j < Lmax; ++j) {
-                if (j < L) {
-                    double z = xs[o + j] * xs[o + j + kk];
-                    double2 a = trig[j];
-                    int j2 = 2 * j;
-                    if (j2 >= W) j2 -= W;
-                    double2 b = trig[j2];
-                    S0 += z;
-                    S1r = fma(z, a.x, S1r);
-                    S1i = fma(z, a.y, S1i);
-                    S2r = fma(z, b.x, S2r);
-                    S2i = fma(z, b.y, S2i);
-                }
+    const double *ri = r0inv + (size_t)seg * env_stride;
+    // the warp's longest window (smallest k) bounds the uniform rebuild loop
+    const int Lmax = W - min(W - 1, kb + (int)(threadIdx.x & ~31u));
+    double acc = 0.0;
+    int t = t0;
+    while (t < t1) {
+        // ---- rebuild the three running sums at frame t
+        const double *xa = xs + (t - t0);
+        double S0 = 0, S1r = 0, S1i = 0, S2r = 0, S2i = 0;
+        for (int j = 0; j < Lmax; ++j) {
+            if (j < L) {
+                const double z = xa[j] * xa[j + kk];
+                const double2 a = trig[j];
+                int j2 = 2 * j;
+                if (j2 >= W) j2 -= W;
+                const double2 b = trig[j2];
+                S0 += z;
+                S1r = fma(z, a.x, S1r);
+                S1i = fma(z, a.y, S1i);
+                S2r = fma(z, b.x, S2r);
+                S2i = fma(z, b.y, S2i);
             }
-            need_init = false;
-            runmax = e0;
         }
-        runmax = fmax(runmax, e0);
-        const double R = q0 * S0 + q1r * S1r + q1i * S1i + q2r * S2r + q2i * S2i;
-        // librosa.util.normalize(norm=inf): frames whose max (= R_t[0]) is below tiny stay unscaled
-        const double inv = (e0 < 2.2250738585072014e-308) ? 1.0 : 1.0 / e0;
-        acc = fma(R, inv, acc);
-        if (t + 1 < t1) {
-            const double zr = xs[o] * xs[o + kk];
-            const double za = xs[o + L] * xs[o + W];
+        double inv = fabs(ri[t]);
+        const double *xk = xa + kk, *xl = xa + L, *xw = xa + W;
+        const double *rn = ri + t + 1;
+        double nx = *rn;  // one frame ahead (the entry after the last frame is never used, but it is inside the workspace)
+        // ---- slide until the chunk ends or the next frame asks for a rebuild
+        for (;;) {
+            const double R = q0 * S0 + q1r * S1r + q1i * S1i + q2r * S2r + q2i * S2i;
+            acc = fma(R, inv, acc);
+            if (++t >= t1) break;
+            const double cur = nx;
+            nx = *++rn;
+            if (__double2hiint(cur) < 0) break;  // sign set (or a NaN with it): rebuild at t
+            inv = cur;
+            const double zr = (*xa++) * (*xk++);
+            const double za = (*xl++) * (*xw++);
             S0 = S0 - zr + za;
             const double a1 = fma(za, eL.x, S1r - zr), b1 = fma(za, eL.y, S1i);
             S1r = a1 * e1.x + b1 * e1.y;
@@ -210,13 +253,7 @@ __device__ __forceinline__ double tg_score(const double *__restrict__ partial, i
     return log1p(1e6 * tg) + (-0.5 * (d * d));
 }
 
-__device__ __forceinline__ int2 block_align(int klo, int khi, int k_min, int W) {  // [klo, khi] → block-aligned [x, y)
-    const int b0 = (klo - k_min) / kLagThreads, b1 = (khi - k_min) / kLagThreads;
-    int y = k_min + (b1 + 1) * kLagThreads;
-    return make_int2(k_min + b0 * kLagThreads, y);
-}
-
-// phase-1 range: the lag blocks within ±half an octave of the prior centre (one thread per segment)
+// phase-1 range: the lags within ±half an octave of the prior centre, [x, y) (one thread per segment)
 __global__ void tg_range_kernel(int n_seg, int W, int k_min, int hop, int sr, const double *__restrict__ start_bpm,
                                 int2 *__restrict__ range1) {
     const int seg = blockIdx.x * blockDim.x + threadIdx.x;
@@ -226,7 +263,7 @@ __global__ void tg_range_kernel(int n_seg, int W, int k_min, int hop, int sr, co
     if (!(k0 == k0) || k0 <= 0.0) klo = khi = k_min;
     klo = klo < k_min ? k_min : (klo > W - 1 ? W - 1 : klo);
     khi = khi < klo ? klo : (khi > W - 1 ? W - 1 : khi);
-    range1[seg] = block_align(klo, khi, k_min, W);
+    range1[seg] = make_int2(klo, khi + 1);
 }
 
 // after phase 1: s* = best score so far; phase-2 range = hull of lags whose prior alone could still beat it
@@ -274,10 +311,10 @@ __global__ void __launch_bounds__(256) tg_bound_kernel(const int32_t *__restrict
     }
     if (threadIdx.x == 0) {
         int2 r2 = r1;
-        if (s_hi[0] >= 0) r2 = block_align(s_lo[0], s_hi[0], k_min, W);
+        if (s_hi[0] >= 0) r2 = make_int2(s_lo[0], s_hi[0] + 1);
         range2[seg] = r2;
         hull[seg] = make_int2(min(r1.x, r2.x), max(r1.y, r2.y));
-        // blocks between r1 and r2 (if disjoint) must be evaluated too so that the hull holds no garbage
+        // lags between r1 and r2 (if disjoint) must be evaluated too so that the hull holds no garbage
         range2[seg] = hull[seg];
     }
 }
@@ -346,7 +383,7 @@ extern "C" size_t ncfa_tempo_workspace_bytes(int n_seg, int max_env_len, int win
     const int chunk = tempo_chunk(max_env_len);
     const size_t n_chunks = (max_env_len + chunk - 1) / chunk;
     return align_up((size_t)win_length * sizeof(double2), 256) + align_up((size_t)win_length * 8, 256) +
-           align_up((size_t)n_seg * max_env_len * 8, 256) + align_up((size_t)n_seg * n_chunks * win_length * 8, 256) +
+           2 * align_up((size_t)n_seg * max_env_len * 8, 256) + align_up((size_t)n_seg * n_chunks * win_length * 8, 256) +
            3 * align_up((size_t)n_seg * sizeof(int2), 256);
 }
 
@@ -372,6 +409,8 @@ extern "C" int ncfa_tempo_lag_batched(const float *d_onset, const int64_t *d_ons
     double *w2 = (double *)wp;
     wp += align_up((size_t)W * 8, 256);
     double *r0 = (double *)wp;
+    wp += align_up((size_t)n_seg * max_env_len * 8, 256);
+    double *r0inv = (double *)wp;
     wp += align_up((size_t)n_seg * max_env_len * 8, 256);
     double *partial = (double *)wp;
     wp += align_up((size_t)n_seg * n_chunks * W * 8, 256);
@@ -402,7 +441,7 @@ extern "C" int ncfa_tempo_lag_batched(const float *d_onset, const int64_t *d_ons
         }
         {
             ProfScope _p("tg_r0_kernel", st);
-            tg_r0_kernel<<<g, kR0Threads, sh, st>>>(d_onset, d_onset_off, d_env_len, max_env_len, W, trig, w2, r0);
+            tg_r0_kernel<<<g, kR0Threads, sh, st>>>(d_onset, d_onset_off, d_env_len, max_env_len, W, trig, w2, r0, r0inv);
         }
         NCFA_LAUNCH_OK("tg_r0_kernel");
     }
@@ -417,11 +456,17 @@ extern "C" int ncfa_tempo_lag_batched(const float *d_onset, const int64_t *d_ons
             int rc = ensure_dynamic_smem((const void *)tg_lag_kernel, sh);
             if (rc) return rc;
         }
+        {
+            const int warps = n_seg * n_chunks;
+            ProfScope _p("tg_flags_kernel", st);
+            tg_flags_kernel<<<(warps + 3) / 4, 128, 0, st>>>(d_env_len, max_env_len, chunk, n_chunks, n_seg, r0, r0inv);
+        }
+        NCFA_LAUNCH_OK("tg_flags_kernel");
         dim3 g((W - k_min + kLagThreads - 1) / kLagThreads, n_chunks, n_seg);
         {
             ProfScope _p("tg_lag_kernel", st);
-            tg_lag_kernel<<<g, kLagThreads, sh, st>>>(d_onset, d_onset_off, d_env_len, max_env_len, W, chunk, n_chunks,
-                                                  k_min, trig, r0, range1, nullptr, partial);
+            tg_lag_kernel<<<g, kLagThreads, sh, st>>>(d_onset, d_onset_off, d_env_len, max_env_len, W, chunk, n_chunks, trig,
+                                                  r0inv, range1, nullptr, partial);
         }
         NCFA_LAUNCH_OK("tg_lag_kernel");
         {
@@ -432,8 +477,8 @@ extern "C" int ncfa_tempo_lag_batched(const float *d_onset, const int64_t *d_ons
         NCFA_LAUNCH_OK("tg_bound_kernel");
         {
             ProfScope _p("tg_lag_kernel", st);
-            tg_lag_kernel<<<g, kLagThreads, sh, st>>>(d_onset, d_onset_off, d_env_len, max_env_len, W, chunk, n_chunks,
-                                                  k_min, trig, r0, range2, range1, partial);
+            tg_lag_kernel<<<g, kLagThreads, sh, st>>>(d_onset, d_onset_off, d_env_len, max_env_len, W, chunk, n_chunks, trig,
+                                                  r0inv, range2, range1, partial);
         }
         NCFA_LAUNCH_OK("tg_lag_kernel");
     }

@@ -45,6 +45,33 @@ def test_onset_strength_hop64_and_ragged(engine):
     assert np.all(got[2] == 0)
 
 
+def test_onset_tile_form_equals_warp_form(engine, tmp_path):
+    """The default warp-per-frame STFT kernel and the tile form (32-frame tiles, lane = frame in the mel phase;
+    NCFA_STFT_IMPL=tile, read once per process) sum in the same order: identical envelopes, ragged tails included."""
+    import os
+    import subprocess
+    import sys
+    ys = [synth.synth(7, 4.0, SR, bpm=101.0), synth.synth(8, 2.0, SR, bpm=133.0)[:40001]]
+    np.save(tmp_path / "a.npy", ys[0])
+    np.save(tmp_path / "b.npy", ys[1])
+    code = (
+        "import sys, numpy as np\n"
+        f"sys.path[:0] = {[p for p in sys.path if p]!r}\n"
+        "from nightcore_analyzer import _engine\n"
+        "e = _engine.get_engine()\n"
+        f"ys = [np.load(r'{tmp_path}/a.npy'), np.load(r'{tmp_path}/b.npy')]\n"
+        "for hop in (64, 512):\n"
+        "    g = e.onset_strength(ys, hop=hop, sr=22050)\n"
+        f"    np.savez(r'{tmp_path}/tile_%d.npz' % hop, *g)\n")
+    env = dict(os.environ, NCFA_STFT_IMPL="tile")
+    subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=600)
+    for hop in (64, 512):
+        got = engine.onset_strength(ys, hop=hop, sr=SR)
+        ref = np.load(tmp_path / f"tile_{hop}.npz")
+        for i, g in enumerate(got):
+            assert np.array_equal(g, ref[f"arr_{i}"]), (hop, i, float(np.max(np.abs(g - ref[f"arr_{i}"]))))
+
+
 def test_onset_top_db_clamp_active(engine):
     """A window that is silent for its first half exercises the per-segment max − 80 dB floor."""
     y = synth.synth(6, 10.0, SR, bpm=120.0).copy()
