@@ -49,6 +49,12 @@ int ncfa_profile_report(char *buf, size_t cap);
  * current device.  Idempotent and thread-safe; the other entry points call it lazily. */
 int ncfa_init_tables(int sr);
 
+/* Small parameter uploads (segment tables, priors, bootstrap values) that must not queue behind a
+ * bulk host->device copy on the DMA engine: a kernel on `stream` reads `nbytes` from PINNED host
+ * memory (cudaHostAlloc / torch pin_memory; checked with cudaHostGetDevicePointer) and writes
+ * them to d_dst.  h_pinned_src must stay untouched until the stream has passed this call. */
+int ncfa_param_upload(void *d_dst, const void *h_pinned_src, size_t nbytes, void *stream);
+
 /* ---- io.py:38-40,94-110  _rms_db / slice_windows --------------------------------------------
  * d_meansq[i] = mean(x^2) of segment i accumulated in float64 (host finishes 20·log10(sqrt)). */
 int ncfa_window_energy(const float *d_audio, const int64_t *d_seg_off, const int32_t *d_seg_len, int n_seg,

@@ -270,6 +270,41 @@ extern "C" int ncfa_profile_report(char *buf, size_t cap) {
     return NCFA_OK;
 }
 extern "C" const char *ncfa_last_error(void) { return ncfa::g_err; }
+namespace ncfa {
+__global__ void __launch_bounds__(256) param_upload_kernel(unsigned char *__restrict__ dst,
+                                                           const unsigned char *__restrict__ src, size_t nbytes) {
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (size_t)gridDim.x * blockDim.x;
+    if ((((uintptr_t)dst | (uintptr_t)src) & 15u) == 0) {
+        const size_t n16 = nbytes / 16;
+        for (size_t i = tid; i < n16; i += nt) reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(src)[i];
+        for (size_t i = n16 * 16 + tid; i < nbytes; i += nt) dst[i] = src[i];
+    } else {
+        for (size_t i = tid; i < nbytes; i += nt) dst[i] = src[i];
+    }
+}
+}  // namespace ncfa
+
+extern "C" int ncfa_param_upload(void *d_dst, const void *h_pinned_src, size_t nbytes, void *stream) {
+    using namespace ncfa;
+    if (nbytes == 0) return NCFA_OK;
+    NCFA_REQUIRE(d_dst && h_pinned_src, "null pointer");
+    void *dsrc = nullptr;
+    if (cudaHostGetDevicePointer(&dsrc, const_cast<void *>(h_pinned_src), 0) != cudaSuccess) {
+        (void)cudaGetLastError();
+        set_error("ncfa_param_upload: source is not pinned, device-mapped host memory");
+        return NCFA_E_INVALID;
+    }
+    const size_t vecs = (nbytes + 15) / 16;
+    const int grid = (int)std::min<size_t>(64, (vecs + 255) / 256);
+    {
+        ProfScope _p("param_upload_kernel", (cudaStream_t)stream);
+        param_upload_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((unsigned char *)d_dst, (const unsigned char *)dsrc,
+                                                                nbytes);
+    }
+    NCFA_LAUNCH_OK("param_upload_kernel");
+    return NCFA_OK;
+}
+
 extern "C" int ncfa_init_tables(int sr) {
     ncfa::Tables t;
     return ncfa::get_tables(sr, &t);

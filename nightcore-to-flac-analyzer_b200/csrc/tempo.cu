@@ -17,6 +17,7 @@
 // yields a best score s*; phase 2 evaluates only the remaining blocks that contain a lag with
 // prior_k > s* − log1p(1e6) − 1e-6 (the prior is unimodal, so that set is one interval).  Lags outside
 // cannot win, so the argmax is unchanged; typically ~80 % of the 2691 hop-64 lags are never touched.
+#include <stdlib.h>
 #include "ncfa_common.cuh"
 
 namespace ncfa {
@@ -372,7 +373,15 @@ __global__ void __launch_bounds__(256) tg_argmax_kernel(const float *__restrict_
     if (threadIdx.x == 0) lag_out[seg] = (s_idx[0] == 0x7fffffff) ? k_min : s_idx[0];
 }
 
-static int tempo_chunk(int max_env_len) { return max_env_len <= 1024 ? (max_env_len < 1 ? 1 : max_env_len) : 4096; }
+static int tempo_chunk(int max_env_len) {
+    if (max_env_len <= 1024) return max_env_len < 1 ? 1 : max_env_len;
+    static const int long_chunk = [] {
+        const char *e = getenv("NCFA_TG_CHUNK");  // experiments only
+        const int v = e ? atoi(e) : 0;
+        return (v >= 1024 && v <= 16384) ? v : 4096;
+    }();
+    return long_chunk;
+}
 
 }  // namespace ncfa
 
@@ -464,7 +473,7 @@ extern "C" int ncfa_tempo_lag_batched(const float *d_onset, const int64_t *d_ons
         NCFA_LAUNCH_OK("tg_flags_kernel");
         dim3 g((W - k_min + kLagThreads - 1) / kLagThreads, n_chunks, n_seg);
         {
-            ProfScope _p("tg_lag_kernel", st);
+            ProfScope _p(n_chunks > 1 ? "tg_lag_kernel[long]" : "tg_lag_kernel", st);
             tg_lag_kernel<<<g, kLagThreads, sh, st>>>(d_onset, d_onset_off, d_env_len, max_env_len, W, chunk, n_chunks, trig,
                                                   r0inv, range1, nullptr, partial);
         }
@@ -476,7 +485,7 @@ extern "C" int ncfa_tempo_lag_batched(const float *d_onset, const int64_t *d_ons
         }
         NCFA_LAUNCH_OK("tg_bound_kernel");
         {
-            ProfScope _p("tg_lag_kernel", st);
+            ProfScope _p(n_chunks > 1 ? "tg_lag_kernel[long]" : "tg_lag_kernel", st);
             tg_lag_kernel<<<g, kLagThreads, sh, st>>>(d_onset, d_onset_off, d_env_len, max_env_len, W, chunk, n_chunks, trig,
                                                   r0inv, range2, range1, partial);
         }

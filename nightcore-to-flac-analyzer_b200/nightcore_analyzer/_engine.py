@@ -7,6 +7,7 @@ tensors and never synchronises; the list-of-numpy convenience wrappers upload, r
 from __future__ import annotations
 
 import math
+import os
 import threading
 from typing import List, Optional, Sequence, Tuple
 
@@ -18,10 +19,12 @@ from ._native import check, lib
 
 # Intermediate log-mel tiles are sized to stay resident in the 126 MB L2 between the STFT kernel
 # and the flux kernel (DESIGN.md "onset front-end").
-ONSET_WS_TARGET_BYTES = 96 << 20
+ONSET_WS_TARGET_BYTES = int(os.environ.get("NCFA_ONSET_WS_MB", "96")) << 20
 MAX_SEGS_PER_CALL = 65535
 # tuning peak lists / decimation pyramids of one launch (HBM scratch, reused across sub-batches)
 CHROMA_WS_TARGET_BYTES = 4 << 30
+# pinned staging ring for parameter uploads (to_dev)
+PARAM_RING_BYTES = 128 << 20
 
 
 def _ptr(t: Optional[torch.Tensor]) -> int:
@@ -36,6 +39,8 @@ class Engine:
         self._ws: dict = {}
         self._lock = threading.Lock()
         self.launches = 0  # kernels launched through this engine (bench.py's gpu_launches)
+        self._ring: Optional[torch.Tensor] = None  # pinned parameter ring (to_dev)
+        self._ring_pos = 0
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
@@ -53,11 +58,38 @@ class Engine:
         return t
 
     def to_dev(self, a: np.ndarray, dtype=None) -> torch.Tensor:
+        """Host array → device tensor on the current stream.  Parameter-sized arrays (segment tables, priors, bootstrap
+        values) do not use the DMA engine: a copy queued there waits behind any bulk audio upload in flight (65 ms for
+        a 125-pair sub-batch) and every such wait is a hole in the kernel stream.  They are written into a pinned ring
+        and moved by a small kernel that reads the ring over PCIe (ncfa_param_upload)."""
         t = torch.from_numpy(np.ascontiguousarray(a))
         if dtype is not None:
             t = t.to(dtype)
-        self.h2d_bytes += t.numel() * t.element_size()
-        return t.to(self.device, non_blocking=True)
+        nbytes = t.numel() * t.element_size()
+        self.h2d_bytes += nbytes
+        if nbytes == 0 or nbytes > PARAM_RING_BYTES // 8:
+            return t.to(self.device, non_blocking=True)
+        out = torch.empty(t.shape, dtype=t.dtype, device=self.device)
+        off = self._ring_reserve(nbytes)
+        self._ring[off : off + nbytes].copy_(t.reshape(-1).view(torch.uint8))
+        with torch.cuda.device(self.device):
+            check(lib.ncfa_param_upload(out.data_ptr(), self._ring.data_ptr() + off, nbytes, self._stream()),
+                  "ncfa_param_upload")
+        return out
+
+    def _ring_reserve(self, nbytes: int) -> int:
+        """16-byte aligned slot of the pinned parameter ring.  Slots are reused only after a wrap, and a wrap waits for
+        the device once (every PARAM_RING_BYTES of parameters, i.e. every few dozen sub-batches)."""
+        if self._ring is None:
+            self._ring = torch.empty(PARAM_RING_BYTES, dtype=torch.uint8, pin_memory=True)
+            self._ring_pos = 0
+        need = (nbytes + 15) // 16 * 16
+        if self._ring_pos + need > PARAM_RING_BYTES:
+            torch.cuda.synchronize(self.device)
+            self._ring_pos = 0
+        off = self._ring_pos
+        self._ring_pos += need
+        return off
 
     def to_host(self, t: torch.Tensor) -> np.ndarray:
         self.d2h_bytes += t.numel() * t.element_size()

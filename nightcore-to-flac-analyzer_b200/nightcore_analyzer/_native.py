@@ -34,6 +34,7 @@ _SIGNATURES = {
     "ncfa_version": (c_int, []),
     "ncfa_last_error": (ctypes.c_char_p, []),
     "ncfa_init_tables": (c_int, [c_int]),
+    "ncfa_param_upload": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "ncfa_profile_enable": (None, [c_int]),
     "ncfa_profile_report": (c_int, [ctypes.c_char_p, c_size_t]),
     "ncfa_window_energy": (c_int, [_P, _P, _P, c_int, _P, _P]),

@@ -289,20 +289,24 @@ def run_batch_arrays(pairs: Sequence[Tuple[np.ndarray, np.ndarray]], sr: int = S
     return analyse_staged(stage_pairs(pairs, sr), **kwargs)
 
 
-def plan_subbatches(n_pairs: int, sub: int, workers: int = 2) -> List[int]:
-    """Sub-batch sizes for ``n_pairs`` pairs: full sub-batches of ``sub`` pairs, preceded by one quarter-size sub-batch
-    per worker so that the first kernels start after a short upload instead of a full one (the head of the pipeline
-    is the only part of the H2D traffic that cannot overlap compute)."""
+def plan_subbatches(n_pairs: int, sub: int, workers: int = 2, first: int = 8, growth: float = 1.5) -> List[int]:
+    """Sub-batch sizes for ``n_pairs`` pairs, at most ``sub`` each.  A job can start only when its upload is complete,
+    and the upload of a worker's next job runs while its current one computes; the copy engine moves a pair about twice
+    as fast as the kernels analyse one, so sizes grow geometrically (``first``, x ``growth`` < 2) until they reach
+    ``sub``: every upload hides behind the compute of the jobs before it and only the first few pairs' copy is
+    exposed.  The rest is split evenly (no short tail job)."""
     sizes: List[int] = []
     left = int(n_pairs)
-    head = max(1, sub // 4)
-    for _ in range(workers):
-        if left > sub:
-            sizes.append(min(head, left))
-            left -= sizes[-1]
-    while left > 0:
-        sizes.append(min(sub, left))
-        left -= sizes[-1]
+    sub = max(1, int(sub))
+    s = float(max(1, first))
+    while int(s) < sub and left - int(s) >= sub:
+        sizes.append(int(s))
+        left -= int(s)
+        s *= growth
+    if left > 0:
+        k = -(-left // sub)
+        base, r = divmod(left, k)
+        sizes += [base + 1] * r + [base] * (k - r)
     return sizes
 
 
@@ -352,9 +356,9 @@ def run_subbatches(jobs: Sequence, fn, workers: int = 2, prepare=None) -> list:
     if workers == 1:
         work(0)
     else:
-        with cf.ThreadPoolExecutor(max_workers=workers) as pool:
-            for f in [pool.submit(work, w) for w in range(workers)]:
-                f.result()
+        # one persistent host thread per worker index: its engine (workspaces, pinned parameter ring) is built once
+        for f in [_worker_thread(device, w).submit(work, w) for w in range(workers)]:
+            f.result()
     for st in streams:
         main.wait_stream(st)
     return out
@@ -410,6 +414,17 @@ def analyse_resident(batches: Sequence[StagedBatch], stats: Optional[dict] = Non
 
 _WORKER_STREAMS: dict = {}
 _UPLOAD_BUFFERS: dict = {}
+
+
+_WORKER_THREADS: dict = {}
+
+
+def _worker_thread(device, w: int):
+    import concurrent.futures as cf
+    key = (torch.device(device).index, w)
+    if key not in _WORKER_THREADS:
+        _WORKER_THREADS[key] = cf.ThreadPoolExecutor(max_workers=1, thread_name_prefix=f"ncfa-worker{w}")
+    return _WORKER_THREADS[key]
 
 
 def _worker_stream(device, w: int) -> "torch.cuda.Stream":
