@@ -188,6 +188,10 @@ int ncfa_spectral_stats_batched(const float *d_audio, const int64_t *d_seg_off, 
  * h_K[1024][72] = the CQT contraction matrix of tuning index j; h_taps[127] = the half-band FIR. */
 int ncfa_host_cqt_matrix(int sr, int tuning_index, float *h_K);
 int ncfa_host_halfband_taps(double *h_taps);
+/* Lane-transposed Slaney mel bank of the STFT kernels: h_lane_bin0 int32[4][32] first bin read by lane l of
+ * group q (bands l, 63-l, 64+l, 127-l), h_qw int32[4] rows per group, h_wt float32[128][32] weights
+ * (row = group offset + i, column = lane; zero outside a band's support). */
+int ncfa_host_mel_lanes(int sr, int32_t *h_lane_bin0, int32_t *h_qw, float *h_wt);
 
 #ifdef __cplusplus
 }

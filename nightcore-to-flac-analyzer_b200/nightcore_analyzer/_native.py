@@ -69,6 +69,7 @@ _SIGNATURES = {
     "ncfa_spectral_stats_batched": (c_int, [_P, _P, _P, c_int, c_int, _P, _P, _P, c_size_t, _P]),
     "ncfa_host_cqt_matrix": (c_int, [c_int, c_int, _P]),
     "ncfa_host_halfband_taps": (c_int, [_P]),
+    "ncfa_host_mel_lanes": (c_int, [c_int, _P, _P, _P]),
 }
 
 

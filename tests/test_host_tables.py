@@ -48,3 +48,29 @@ def test_cqt_matrix_rejects_bad_arguments(lib):
     assert lib.ncfa_host_cqt_matrix(96000, 50, K.ctypes.data) < 0      # top-octave filters no longer fit n_fft 1024
     from nightcore_analyzer import _native
     assert "1024" in _native.last_error()
+
+
+@pytest.mark.parametrize("sr", [22050, 44100, 11025, 16000])
+def test_mel_lane_table_is_the_slaney_bank_and_conflict_free(lib, sr):
+    """The lane-transposed mel bank of the STFT kernels: (1) scattering it back gives the restated
+    librosa.filters.mel matrix exactly (float32); (2) within a group the 32 lanes start at distinct
+    residues mod 32, so the lock-step reads of the power spectrum never share a shared-memory bank."""
+    lb = np.zeros(128, np.int32)
+    qw = np.zeros(4, np.int32)
+    wt = np.zeros((128, 32), np.float32)
+    assert lib.ncfa_host_mel_lanes(sr, lb.ctypes.data, qw.ctypes.data, wt.ctypes.data) == 0
+    want = lr.mel_filter(sr, 2048, 128).astype(np.float32)
+    got = np.zeros((128, 1025 + 256), np.float32)
+    off = 0
+    for q in range(4):
+        starts = lb[q * 32:(q + 1) * 32]
+        assert starts.min() >= 0
+        assert len(set(int(b) % 32 for b in starts)) == 32, (sr, q, sorted(int(b) % 32 for b in starts))
+        for lane in range(32):
+            band = [lane, 63 - lane, 64 + lane, 127 - lane][q]
+            b0 = int(starts[lane])
+            got[band, b0:b0 + qw[q]] = wt[off:off + qw[q], lane]
+        off += int(qw[q])
+    assert off <= 128
+    assert np.all(got[:, 1025:] == 0)
+    assert np.array_equal(got[:, :1025], want)
