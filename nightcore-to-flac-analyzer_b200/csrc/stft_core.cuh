@@ -33,8 +33,7 @@ __device__ __forceinline__ cf mul_w64(cf a) {
     if constexpr (K2 == 0) {
         return a;
     } else {
-        // a · (c - i s)
-        return cf{a.x * C[K2] + a.y * S[K2], a.y * C[K2] - a.x * S[K2]};
+        return cmul_cs(a, C[K2], S[K2]);  // a · (c - i s)
     }
 }
 
@@ -52,10 +51,10 @@ struct PostStage {
         p.x = __shfl_sync(0xffffffffu, snd.x, src);
         p.y = __shfl_sync(0xffffffffu, snd.y, src);
         if (lane == 0) p = own;
-        cf e = cf{0.5f * (zk.x + p.x), 0.5f * (zk.y - p.y)};
-        cf o = cf{0.5f * (zk.y + p.y), -0.5f * (zk.x - p.x)};
+        cf e = cscale(cadd_conj(zk, p), 0.5f);            // ½(Z[k] + conj Z[N−k])
+        cf o = cscale(cmul_mi(csub_conj(zk, p)), 0.5f);   // (Z[k] − conj Z[N−k]) / (2i)
         cf w = mul_w64<K2>(twl);  // W_2048^(lane + 32·K2)
-        cf wo = cmul(w, o);
+        cf wo = cmul(o, w);
         cf x = cadd(e, wo);
         cf y = csub(e, wo);
         pw[lane + 32 * K2] = x.x * x.x + x.y * x.y;
@@ -106,7 +105,7 @@ __device__ __forceinline__ void warp_power_spectrum_global(const float *__restri
         for (int n1 = 0; n1 < 32; ++n1) {
             const float2 xs = __ldg(reinterpret_cast<const float2 *>(fr + 64 * n1 + 2 * lane));
             const float2 ws = *reinterpret_cast<const float2 *>(hann + 64 * n1 + 2 * lane);
-            v[n1] = cf{xs.x * ws.x, xs.y * ws.y};
+            v[n1] = cmul_elem(cf{xs.x, xs.y}, cf{ws.x, ws.y});
         }
     } else {
 #pragma unroll
@@ -115,7 +114,7 @@ __device__ __forceinline__ void warp_power_spectrum_global(const float *__restri
             const float x0 = (p >= 0 && p < len) ? __ldg(src + p) : 0.0f;
             const float x1 = (p + 1 >= 0 && p + 1 < len) ? __ldg(src + p + 1) : 0.0f;
             const float2 ws = *reinterpret_cast<const float2 *>(hann + 64 * n1 + 2 * lane);
-            v[n1] = cf{x0 * ws.x, x1 * ws.y};
+            v[n1] = cmul_elem(cf{x0, x1}, cf{ws.x, ws.y});
         }
     }
     warp_power_spectrum_regs(v, tw, scr, twl, lane);
@@ -139,10 +138,10 @@ struct PostStageTile {
         p.x = __shfl_sync(0xffffffffu, snd.x, src);
         p.y = __shfl_sync(0xffffffffu, snd.y, src);
         if (lane == 0) p = own;
-        cf e = cf{0.5f * (zk.x + p.x), 0.5f * (zk.y - p.y)};
-        cf o = cf{0.5f * (zk.y + p.y), -0.5f * (zk.x - p.x)};
+        cf e = cscale(cadd_conj(zk, p), 0.5f);            // ½(Z[k] + conj Z[N−k])
+        cf o = cscale(cmul_mi(csub_conj(zk, p)), 0.5f);   // (Z[k] − conj Z[N−k]) / (2i)
         cf w = mul_w64<K2>(twl);  // W_2048^(lane + 32·K2)
-        cf wo = cmul(w, o);
+        cf wo = cmul(o, w);
         cf x = cadd(e, wo);
         cf y = csub(e, wo);
         pcol[(lane + 32 * K2) * kPStride] = x.x * x.x + x.y * x.y;
@@ -195,7 +194,7 @@ __device__ __forceinline__ void warp_power_spectrum_global_tile(const float *__r
         for (int n1 = 0; n1 < 32; ++n1) {
             const float2 xs = __ldg(reinterpret_cast<const float2 *>(fr + 64 * n1 + 2 * lane));
             const float2 ws = *reinterpret_cast<const float2 *>(hann + 64 * n1 + 2 * lane);
-            v[n1] = cf{xs.x * ws.x, xs.y * ws.y};
+            v[n1] = cmul_elem(cf{xs.x, xs.y}, cf{ws.x, ws.y});
         }
     } else {
 #pragma unroll
@@ -204,7 +203,7 @@ __device__ __forceinline__ void warp_power_spectrum_global_tile(const float *__r
             const float x0 = (p >= 0 && p < len) ? __ldg(src + p) : 0.0f;
             const float x1 = (p + 1 >= 0 && p + 1 < len) ? __ldg(src + p + 1) : 0.0f;
             const float2 ws = *reinterpret_cast<const float2 *>(hann + 64 * n1 + 2 * lane);
-            v[n1] = cf{x0 * ws.x, x1 * ws.y};
+            v[n1] = cmul_elem(cf{x0, x1}, cf{ws.x, ws.y});
         }
     }
     warp_power_spectrum_regs_tile(v, tw, scr, pcol, twl, lane);
@@ -219,7 +218,7 @@ __device__ __forceinline__ void warp_power_spectrum(const float *fr, const float
     for (int n1 = 0; n1 < 32; ++n1) {
         float2 xs = *reinterpret_cast<const float2 *>(fr + 64 * n1 + 2 * lane);
         float2 ws = *reinterpret_cast<const float2 *>(hann + 64 * n1 + 2 * lane);
-        v[n1] = cf{xs.x * ws.x, xs.y * ws.y};
+        v[n1] = cmul_elem(cf{xs.x, xs.y}, cf{ws.x, ws.y});
     }
     fft32_dif(v);
 #pragma unroll
