@@ -77,37 +77,30 @@ __device__ double select_localmax(const double *cum, int n, int rank, int *hist,
     return ordered_to_f64(*s_prefix);
 }
 
-__global__ void beat_track_kernel(const float *__restrict__ onset, const int64_t *__restrict__ onset_off,
-                                  const int32_t *__restrict__ env_len, int env_stride, const int32_t *__restrict__ lag,
-                                  double *__restrict__ ws_f64, int32_t *__restrict__ ws_i32, int max_fpb,
-                                  int32_t *__restrict__ beats_out, int max_beats, int32_t *__restrict__ n_beats,
-                                  int ring) {
-    // blockDim doubles (reductions) | ring doubles: cumulative scores of the last `ring` frames (power of two >=
-    // far + near for every admissible fpb) | transition penalties for d = near .. far
-    extern __shared__ double sh_d[];
-    double *cring = sh_d + blockDim.x;
-    double *pen = cring + ring;
-    const int rmask = ring - 1;
-    __shared__ int hist[256];
-    __shared__ unsigned long long s_prefix;
-    __shared__ int s_rank, s_cnt, s_n0, s_n1;
-    __shared__ double s_thr;
+// Workspace of one segment (doubles): onorm[env_stride] | ls[env_stride] | cum[env_stride] | window[2·max_fpb+1] |
+// (2·max_fpb+1 unused) | 8 spare — spare[0] holds max(ls) as an order-preserving 64-bit key.
+__device__ __forceinline__ double *beat_seg_base(double *ws_f64, int seg, int env_stride, int max_fpb) {
+    const size_t K = 2 * (size_t)max_fpb + 1;
+    return ws_f64 + (size_t)seg * (3 * (size_t)env_stride + 2 * K + 8);
+}
+
+// pass 1 (one CTA per envelope): onsets / (std(ddof=1) + tiny) and the Gaussian window exp(-½((k-fpb)·32/fpb)²)
+__global__ void __launch_bounds__(256) beat_prep_kernel(const float *__restrict__ onset,
+                                                        const int64_t *__restrict__ onset_off,
+                                                        const int32_t *__restrict__ env_len, int env_stride,
+                                                        const int32_t *__restrict__ lag, double *__restrict__ ws_f64,
+                                                        int max_fpb) {
+    __shared__ double sh_d[256];
     const int seg = blockIdx.x;
     const int N = env_len[seg];
     const int fpb = lag[seg];
+    if (fpb < 2 || fpb > max_fpb || N < 2) return;
     const float *on = onset + onset_off[seg];
     const int tid = threadIdx.x, nt = blockDim.x;
-    if (fpb < 2 || fpb > max_fpb || N < 2) {
-        if (tid == 0) n_beats[seg] = 0;
-        return;
-    }
-    // workspace carve-up (per segment)
     const size_t K = 2 * (size_t)max_fpb + 1;
-    double *base = ws_f64 + (size_t)seg * (3 * (size_t)env_stride + 2 * K + 8);
-    double *onorm = base, *ls = base + env_stride, *cum = base + 2 * (size_t)env_stride;
-    double *window = base + 3 * (size_t)env_stride;
-    int32_t *backlink = ws_i32 + (size_t)seg * 2 * env_stride, *tmp = backlink + env_stride;
-
+    double *base = beat_seg_base(ws_f64, seg, env_stride, max_fpb);
+    double *onorm = base, *window = base + 3 * (size_t)env_stride;
+    if (tid == 0) *reinterpret_cast<unsigned long long *>(window + 2 * K) = f64_to_ordered(-INFINITY);
     // ---- onsets / (std(ddof=1) + tiny)
     double s = 0.0;
     for (int i = tid; i < N; i += nt) s += (double)on[i];
@@ -121,13 +114,111 @@ __global__ void beat_track_kernel(const float *__restrict__ onset, const int64_t
     const double denom = sqrt(var) + 2.2250738585072014e-308;
     for (int i = tid; i < N; i += nt) onorm[i] = (double)on[i] / denom;
 
-    // ---- tables: Gaussian window exp(-½((k-fpb)·32/fpb)²) and transition penalty 100·(ln d − ln fpb)²
     const int Kw = 2 * fpb + 1;
     const double dfpb = (double)fpb;
     for (int k = tid; k < Kw; k += nt) {
         double a = ((double)(k - fpb) * 32.0) / dfpb;
         window[k] = exp(-0.5 * (a * a));
     }
+}
+
+// pass 2 (all frames of all envelopes in parallel): local score = 'same' convolution of the normalised onsets with
+// the window, restated with librosa's loop bounds (ascending k, unfused multiply-add), and its maximum per envelope
+constexpr int kScoreFramesPerThread = 4;  // the sliding window below is written for 4
+__global__ void __launch_bounds__(256) beat_score_kernel(const int32_t *__restrict__ env_len, int env_stride,
+                                                         const int32_t *__restrict__ lag, double *__restrict__ ws_f64,
+                                                         int max_fpb) {
+    __shared__ double sh_d[256];
+    const int seg = blockIdx.x;
+    const int N = env_len[seg];
+    const int fpb = lag[seg];
+    if (fpb < 2 || fpb > max_fpb || N < 2) return;
+    const int i0 = blockIdx.y * (256 * kScoreFramesPerThread);
+    if (i0 >= N) return;
+    const size_t K = 2 * (size_t)max_fpb + 1;
+    double *base = beat_seg_base(ws_f64, seg, env_stride, max_fpb);
+    const double *onorm = base, *window = base + 3 * (size_t)env_stride;
+    double *ls = base + env_stride;
+    const int Kw = 2 * fpb + 1;
+    double lmax = -INFINITY;
+    // a thread owns kScoreFramesPerThread CONSECUTIVE frames: away from the envelope's ends all of them run over the
+    // full window, so one window load and one new onset load feed four multiply-adds (register sliding window); every
+    // frame still adds its products in ascending k, exactly like the one-frame loop used at the ends
+    const int ib = i0 + (int)threadIdx.x * kScoreFramesPerThread;
+    if (ib < N) {
+        if (ib + fpb >= Kw && ib + kScoreFramesPerThread - 1 + fpb - N + 1 <= 0) {
+            // acc_r = Σ_k window[k]·onorm[ib + r + fpb − k]: with x_j = onorm[ib + fpb − k + j], step k → k+1 shifts x down
+            const double *xo = onorm + ib + fpb;
+            double x0 = xo[0], x1 = xo[1], x2 = xo[2], x3 = xo[3];
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            for (int k = 0; k < Kw; ++k) {
+                const double w = window[k];
+                a0 = a0 + w * x0;
+                a1 = a1 + w * x1;
+                a2 = a2 + w * x2;
+                a3 = a3 + w * x3;
+                x3 = x2;
+                x2 = x1;
+                x1 = x0;
+                x0 = xo[-(k + 1)];
+            }
+            ls[ib] = a0;
+            ls[ib + 1] = a1;
+            ls[ib + 2] = a2;
+            ls[ib + 3] = a3;
+            lmax = fmax(fmax(a0, a1), fmax(a2, a3));
+        } else {
+            for (int r = 0; r < kScoreFramesPerThread; ++r) {
+                const int i = ib + r;
+                if (i >= N) break;
+                int k0 = i + fpb - N + 1;
+                if (k0 < 0) k0 = 0;
+                int k1 = i + fpb;
+                if (k1 > Kw) k1 = Kw;
+                double acc = 0.0;
+                for (int k = k0; k < k1; ++k) acc = acc + window[k] * onorm[i + fpb - k];
+                ls[i] = acc;
+                lmax = fmax(lmax, acc);
+            }
+        }
+    }
+    lmax = block_reduce(lmax, sh_d, [](double a, double b) { return fmax(a, b); });
+    if (threadIdx.x == 0)
+        atomicMax(reinterpret_cast<unsigned long long *>(base + 3 * (size_t)env_stride + 2 * K), f64_to_ordered(lmax));
+}
+
+__global__ void beat_track_kernel(const float *__restrict__ onset, const int64_t *__restrict__ onset_off,
+                                  const int32_t *__restrict__ env_len, int env_stride, const int32_t *__restrict__ lag,
+                                  double *__restrict__ ws_f64, int32_t *__restrict__ ws_i32, int max_fpb,
+                                  int32_t *__restrict__ beats_out, int max_beats, int32_t *__restrict__ n_beats,
+                                  int ring) {
+    // blockDim doubles (reductions) | ring doubles: cumulative scores of the last `ring` frames (power of two >=
+    // far + near for every admissible fpb) | transition penalties for d = near .. far
+    extern __shared__ double sh_d[];
+    double *cring = sh_d + blockDim.x;
+    double *pen = cring + ring;
+    const int rmask = ring - 1;
+    __shared__ int hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_rank, s_cnt;
+    __shared__ double s_thr;
+    const int seg = blockIdx.x;
+    const int N = env_len[seg];
+    const int fpb = lag[seg];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (fpb < 2 || fpb > max_fpb || N < 2) {
+        if (tid == 0) n_beats[seg] = 0;
+        return;
+    }
+    // workspace carve-up (per segment)
+    const size_t K = 2 * (size_t)max_fpb + 1;
+    double *base = ws_f64 + (size_t)seg * (3 * (size_t)env_stride + 2 * K + 8);
+    double *ls = base + env_stride, *cum = base + 2 * (size_t)env_stride;
+    double *window = base + 3 * (size_t)env_stride;
+    int32_t *backlink = ws_i32 + (size_t)seg * 2 * env_stride, *tmp = backlink + env_stride;
+
+    // (onset normalisation, the Gaussian window and the local score come from beat_prep_kernel / beat_score_kernel)
+    const double dfpb = (double)fpb;
     const int near = (int)rint(dfpb / 2.0);  // np.round: half to even
     const int far = 2 * fpb;
     const double logf = log(dfpb);
@@ -137,19 +228,7 @@ __global__ void beat_track_kernel(const float *__restrict__ onset, const int64_t
     }
     __syncthreads();
 
-    // ---- local score: 'same' convolution restated with librosa's loop bounds
-    double lmax = -INFINITY;
-    for (int i = tid; i < N; i += nt) {
-        int k0 = i + fpb - N + 1;
-        if (k0 < 0) k0 = 0;
-        int k1 = i + fpb;
-        if (k1 > Kw) k1 = Kw;
-        double acc = 0.0;
-        for (int k = k0; k < k1; ++k) acc = acc + window[k] * onorm[i + fpb - k];
-        ls[i] = acc;
-        lmax = fmax(lmax, acc);
-    }
-    lmax = block_reduce(lmax, sh_d, [](double a, double b) { return fmax(a, b); });
+    const double lmax = ordered_to_f64(*reinterpret_cast<const unsigned long long *>(window + 2 * K));
     const double score_thresh = 0.01 * lmax;
     // first frame whose local score reaches the threshold: before it backlink = -1
     int first = N;
@@ -319,6 +398,19 @@ extern "C" int ncfa_beat_track_batched(const float *d_onset, const int64_t *d_on
     const size_t smem = ((size_t)threads + ring + (3 * (size_t)max_lag / 2 + 4)) * sizeof(double);
     int rc = ensure_dynamic_smem((const void *)beat_track_kernel, smem);
     if (rc) return rc;
+    {
+        ProfScope _p("beat_prep_kernel", (cudaStream_t)stream);
+        beat_prep_kernel<<<n_seg, 256, 0, (cudaStream_t)stream>>>(d_onset, d_onset_off, d_env_len, max_env_len, d_lag, wf,
+                                                              max_lag);
+    }
+    NCFA_LAUNCH_OK("beat_prep_kernel");
+    {
+        dim3 g(n_seg, (max_env_len + 256 * kScoreFramesPerThread - 1) / (256 * kScoreFramesPerThread));
+        NCFA_REQUIRE(g.y <= 65535, "envelope too long for one call");
+        ProfScope _p("beat_score_kernel", (cudaStream_t)stream);
+        beat_score_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(d_env_len, max_env_len, d_lag, wf, max_lag);
+    }
+    NCFA_LAUNCH_OK("beat_score_kernel");
     {
         ProfScope _p(max_env_len <= 2048 ? "beat_track_kernel" : "beat_track_kernel[long]", (cudaStream_t)stream);
         beat_track_kernel<<<n_seg, threads, smem, (cudaStream_t)stream>>>(d_onset, d_onset_off, d_env_len, max_env_len,

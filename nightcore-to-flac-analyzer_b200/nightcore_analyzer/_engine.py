@@ -75,6 +75,7 @@ class Engine:
         with torch.cuda.device(self.device):
             check(lib.ncfa_param_upload(out.data_ptr(), self._ring.data_ptr() + off, nbytes, self._stream()),
                   "ncfa_param_upload")
+        self.launches += 1
         return out
 
     def _ring_reserve(self, nbytes: int) -> int:
@@ -213,7 +214,7 @@ class Engine:
                         _ptr(onset), d_env_off.data_ptr() + 8 * s, d_env_len.data_ptr() + 4 * s, e - s, mx, hop, sr,
                         d_start_bpm.data_ptr() + 8 * s, lag.data_ptr() + 4 * s, _ptr(ws), ws.numel(), st),
                     "ncfa_tempo_lag_batched")
-                self.launches += 7
+                self.launches += 8
         return lag[:n_seg]
 
     # ------------------------------------------------------------------ beat tracker
@@ -243,7 +244,7 @@ class Engine:
                                             _ptr(beats), max_beats, _ptr(n_beats), _ptr(ws), ws.numel(),
                                             self._stream()),
                 "ncfa_beat_track_batched")
-            self.launches += 1
+            self.launches += 3  # prep, local score, DP
         return beats[:n_seg], n_beats[:n_seg]
 
     # ------------------------------------------------------------------ fused: segments → (lag, n_beats[, beats])
