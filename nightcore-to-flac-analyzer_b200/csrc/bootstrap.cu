@@ -17,6 +17,8 @@
 
 namespace ncfa {
 
+constexpr int kBootFinishMaxStaged = 5000;  // bootstrap values of one job staged in shared memory (40 KB)
+
 typedef unsigned __int128 u128;
 
 struct LcgStep {
@@ -349,51 +351,60 @@ __global__ void __launch_bounds__(256) boot_median_kernel(
     }
 }
 
-// rank-select the j-th order statistic of v[0..n) (block-cooperative, O(n²/threads))
-__device__ double block_order_stat(const double *v, int n, int j, double *s_val) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const double x = v[i];
-        int r = 0;
-        for (int k = 0; k < n; ++k) {
-            const double y = v[k];
-            r += (y < x || (y == x && k < i)) ? 1 : 0;
-        }
-        if (r == j) *s_val = x;
-    }
-    __syncthreads();
-    return *s_val;
-}
-
-__device__ double np_percentile_linear(const double *v, int n, double q, double *s_val) {
-    // np.percentile(method='linear'): q/100, virtual index (n-1)·quantile, _lerp
+// np.percentile(method='linear') index arithmetic: q/100, virtual index (n-1)·quantile → (prev, next, gamma)
+__device__ __forceinline__ void percentile_indices(int n, double q, int *prev, int *next, double *gamma) {
     const double quant = q / 100.0;
     const double virt = (double)(n - 1) * quant;
-    int prev = (int)floor(virt), next = prev + 1;
-    if (virt >= (double)(n - 1)) prev = next = n - 1;
-    if (virt < 0.0) prev = next = 0;
-    const double gamma = virt - floor(virt);
-    const double a = block_order_stat(v, n, prev, s_val);
-    const double b = block_order_stat(v, n, next, s_val);
+    int p = (int)floor(virt), nx = p + 1;
+    if (virt >= (double)(n - 1)) p = nx = n - 1;
+    if (virt < 0.0) p = nx = 0;
+    *prev = p;
+    *next = nx;
+    *gamma = virt - floor(virt);
+}
+__device__ __forceinline__ double percentile_lerp(double a, double b, double gamma) {  // numpy's _lerp
     const double d = b - a;
     double r = a + d * gamma;
     if (gamma >= 0.5) r = b - d * (1.0 - gamma);
     return r;
 }
 
+// One CTA per job: ONE rank pass over the n_boot bootstrap values (staged in shared memory; rank of element i =
+// #{k : v[k] < v[i] or (v[k] == v[i] and k < i)}, O(n²/threads)) picks the four order statistics that the two
+// percentiles interpolate between.
 __global__ void __launch_bounds__(256) boot_finish_kernel(const int32_t *__restrict__ a_len,
                                                           const int32_t *__restrict__ b_len, int max_a, int max_b,
                                                           int n_boot, const double *__restrict__ sorted_a,
                                                           const double *__restrict__ sorted_b,
                                                           const double *__restrict__ boot, double q_lo, double q_hi,
                                                           double *__restrict__ out) {
-    __shared__ double s_val;
+    extern __shared__ double sv[];  // n_boot values (global memory is read directly when they do not fit)
+    __shared__ double s_stat[4];
     const int job = blockIdx.x;
     const int na = a_len[job], nb = b_len ? b_len[job] : 0;
-    const double *v = boot + (size_t)job * n_boot;
-    const double lo = np_percentile_linear(v, n_boot, q_lo, &s_val);
-    const double hi = np_percentile_linear(v, n_boot, q_hi, &s_val);
+    const double *vg = boot + (size_t)job * n_boot;
+    const bool staged = n_boot <= kBootFinishMaxStaged;
+    if (staged)
+        for (int i = threadIdx.x; i < n_boot; i += blockDim.x) sv[i] = vg[i];
+    __syncthreads();
+    const double *v = staged ? sv : vg;
+    int j[4];
+    double g_lo, g_hi;
+    percentile_indices(n_boot, q_lo, &j[0], &j[1], &g_lo);
+    percentile_indices(n_boot, q_hi, &j[2], &j[3], &g_hi);
+    for (int i = threadIdx.x; i < n_boot; i += blockDim.x) {
+        const double x = v[i];
+        int r = 0;
+        for (int k = 0; k < i; ++k) r += (v[k] <= x) ? 1 : 0;           // y < x or (y == x and k < i)
+        for (int k = i + 1; k < n_boot; ++k) r += (v[k] < x) ? 1 : 0;
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+            if (r == j[m]) s_stat[m] = x;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
+        const double lo = percentile_lerp(s_stat[0], s_stat[1], g_lo);
+        const double hi = percentile_lerp(s_stat[2], s_stat[3], g_hi);
         const double *sa = sorted_a + (size_t)job * max_a;
         double point = (na & 1) ? sa[na >> 1] : (sa[(na - 1) >> 1] + sa[na >> 1]) / 2.0;
         if (nb > 0) {
@@ -523,7 +534,7 @@ extern "C" int ncfa_bootstrap_ratio_batched(const double *d_a, const int64_t *d_
     }
     {
         ProfScope _p("boot_finish_kernel", st);
-        boot_finish_kernel<<<n_jobs, 256, 0, st>>>(d_a_len, d_b ? d_b_len : nullptr, max_a, max_b > 0 ? max_b : 1, n_boot,
+        boot_finish_kernel<<<n_jobs, 256, n_boot <= kBootFinishMaxStaged ? (size_t)n_boot * 8 : 0, st>>>(d_a_len, d_b ? d_b_len : nullptr, max_a, max_b > 0 ? max_b : 1, n_boot,
                                                sorted_a, sorted_b, boot, q_lo, q_hi, d_out);
     }
     NCFA_LAUNCH_OK("boot_finish_kernel");

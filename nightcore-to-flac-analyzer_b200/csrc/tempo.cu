@@ -46,10 +46,13 @@ __global__ void tg_tables_kernel(int W, double2 *__restrict__ trig, double *__re
 
 // pass 1: r0[seg][t] = Σ_j w[j]²·x[t+j]²  — the lag-0 autocorrelation every frame is normalised by.
 // w² = 3/8 − ½cos θj + ⅛cos 2θj, so r0 = ⅜S0 − ½Re S1 + ⅛Re S2 with the same three running sums as the lags
-// (L = W): one thread owns kR0Block consecutive frames, sums them exactly at the first one and slides; whenever
-// the combination cancels (r0 below 1e-3 of its S0 part) the frame is re-summed directly with the w² table.
-constexpr int kR0Block = 128;
-constexpr int kR0Threads = 64;
+// (L = W).  A thread owns kR0Block = 32 consecutive frames: it needs the exact sums at its first frame and slides from
+// there.  The exact sums are assembled from per-block partials shared by the whole CTA — P[b] = Σ_{j<32} z[32b+j]·e^{iθj},
+// S(32t) = Σ_m e^{iθ·32m}·P[t+m] + the W mod 32 tail — i.e. ~90 complex multiply-adds per thread instead of W = 2756
+// terms.  Whenever the combination cancels (r0 below 1e-3 of its S0 part) the frame is re-summed directly with the w²
+// table.
+constexpr int kR0Block = 32;
+constexpr int kR0Threads = 256;
 __device__ __forceinline__ int r0_pad(int i) { return i + (i >> 5); }  // spreads the per-thread streams over banks
 
 __global__ void __launch_bounds__(kR0Threads) tg_r0_kernel(const float *__restrict__ onset,
@@ -57,37 +60,74 @@ __global__ void __launch_bounds__(kR0Threads) tg_r0_kernel(const float *__restri
                                                            const int32_t *__restrict__ env_len, int env_stride, int W,
                                                            const double2 *__restrict__ trig,
                                                            const double *__restrict__ w2, double *__restrict__ r0,
-                                                           double *__restrict__ r0inv) {
-    extern __shared__ double zs[];  // r0_pad(kR0Threads·kR0Block + W) squared padded-envelope samples
+                                                           double *__restrict__ r0inv, int frames_cap) {
+    // frames_cap = frames per CTA (blockDim.x · kR0Block)
+    extern __shared__ double zs[];  // r0_pad(frames_cap + W + 32) squared padded-envelope samples | block partials
     const int seg = blockIdx.y;
     const int n = env_len[seg];
-    const int f0 = blockIdx.x * (kR0Threads * kR0Block);
+    const int f0 = blockIdx.x * frames_cap;
     if (f0 >= n) return;
     const float *on = onset + onset_off[seg];
     const int p = W / 2;
-    const int span = min(kR0Threads * kR0Block, n - f0) + W;
-    for (int i = threadIdx.x; i < span; i += kR0Threads) {
+    const int frames = min(frames_cap, n - f0);
+    const int span = frames + W;
+    const int span_cap = frames_cap + W;
+    double *P = zs + r0_pad(span_cap + 32) + 1;  // [5][n_blocks]: S0, S1r, S1i, S2r, S2i of every 32-sample block
+    const int n_blocks = (span_cap + 31) / 32;
+    for (int i = threadIdx.x; i < n_blocks * 32; i += blockDim.x) {
         const int m = f0 + i;
-        const double v = (m < n + 2 * p) ? padded_env(on, n, p, m) : 0.0;
-        zs[r0_pad(i)] = v * v;
+        const double v = (i < span && m < n + 2 * p) ? padded_env(on, n, p, m) : 0.0;
+        if (i < span_cap + 32) zs[r0_pad(i)] = v * v;
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < n_blocks; b += blockDim.x) {
+        double S0 = 0, S1r = 0, S1i = 0, S2r = 0, S2i = 0;
+        for (int j = 0; j < 32; ++j) {
+            const double z = zs[r0_pad(32 * b + j)];
+            const double2 a = trig[j % W];
+            const double2 c = trig[(2 * j) % W];
+            S0 += z;
+            S1r = fma(z, a.x, S1r);
+            S1i = fma(z, a.y, S1i);
+            S2r = fma(z, c.x, S2r);
+            S2i = fma(z, c.y, S2i);
+        }
+        P[b] = S0;
+        P[n_blocks + b] = S1r;
+        P[2 * n_blocks + b] = S1i;
+        P[3 * n_blocks + b] = S2r;
+        P[4 * n_blocks + b] = S2i;
     }
     __syncthreads();
     const int tb = f0 + threadIdx.x * kR0Block;
     if (tb >= n) return;
     const int te = min(n, tb + kR0Block);
-    const int o0 = tb - f0;
+    const int o0 = tb - f0;  // = 32·threadIdx.x
     double S0 = 0, S1r = 0, S1i = 0, S2r = 0, S2i = 0;
-    for (int j = 0; j < W; ++j) {
+    const int M = W / 32;
+    for (int m = 0; m < M; ++m) {
+        const int b = threadIdx.x + m;
+        const double2 a = trig[32 * m];               // e^{iθ·32m}
+        const double2 c = trig[(64 * m) % W];         // e^{2iθ·32m}
+        const double p1r = P[n_blocks + b], p1i = P[2 * n_blocks + b];
+        const double p2r = P[3 * n_blocks + b], p2i = P[4 * n_blocks + b];
+        S0 += P[b];
+        S1r = fma(p1r, a.x, fma(-p1i, a.y, S1r));
+        S1i = fma(p1r, a.y, fma(p1i, a.x, S1i));
+        S2r = fma(p2r, c.x, fma(-p2i, c.y, S2r));
+        S2i = fma(p2r, c.y, fma(p2i, c.x, S2i));
+    }
+    for (int j = 32 * M; j < W; ++j) {  // the W mod 32 tail
         const double z = zs[r0_pad(o0 + j)];
         const double2 a = trig[j];
         int j2 = 2 * j;
         if (j2 >= W) j2 -= W;
-        const double2 b = trig[j2];
+        const double2 c = trig[j2];
         S0 += z;
         S1r = fma(z, a.x, S1r);
         S1i = fma(z, a.y, S1i);
-        S2r = fma(z, b.x, S2r);
-        S2i = fma(z, b.y, S2i);
+        S2r = fma(z, c.x, S2r);
+        S2i = fma(z, c.y, S2i);
     }
     const double2 e1 = trig[1 % W], e2 = trig[2 % W];
     double *out = r0 + (size_t)seg * env_stride;
@@ -440,17 +480,22 @@ extern "C" int ncfa_tempo_lag_batched(const float *d_onset, const int64_t *d_ons
     }
     NCFA_LAUNCH_OK("tg_tables_kernel");
     {
-        const int per_cta = kR0Threads * kR0Block;
+        // frames per CTA: 8192 for whole tracks, one warp's worth of 32-frame blocks for short envelopes
+        int threads = ((max_env_len + kR0Block - 1) / kR0Block + 31) / 32 * 32;
+        threads = threads < 32 ? 32 : (threads > kR0Threads ? kR0Threads : threads);
+        const int per_cta = threads * kR0Block;
         dim3 g((max_env_len + per_cta - 1) / per_cta, n_seg);
-        const int span_max = (max_env_len < per_cta ? max_env_len : per_cta) + W;
-        size_t sh = (size_t)(span_max + (span_max >> 5) + 2) * 8;
+        const int span_cap = per_cta + W;
+        const int n_blocks = (span_cap + 31) / 32;
+        size_t sh = (size_t)(span_cap + 32 + ((span_cap + 32) >> 5) + 2 + 5 * n_blocks) * 8;
         if (sh > 48 * 1024) {
             int rc = ensure_dynamic_smem((const void *)tg_r0_kernel, sh);
             if (rc) return rc;
         }
         {
             ProfScope _p("tg_r0_kernel", st);
-            tg_r0_kernel<<<g, kR0Threads, sh, st>>>(d_onset, d_onset_off, d_env_len, max_env_len, W, trig, w2, r0, r0inv);
+            tg_r0_kernel<<<g, threads, sh, st>>>(d_onset, d_onset_off, d_env_len, max_env_len, W, trig, w2, r0, r0inv,
+                                                 per_cta);
         }
         NCFA_LAUNCH_OK("tg_r0_kernel");
     }
