@@ -466,14 +466,17 @@ __global__ void __launch_bounds__(256) tuning_pick_kernel(const int32_t *__restr
 //     out[t] = h[63]·xe[t] + Σ_{m<64} h[2m]·xo[t + m − 32],   xe[j] = in[2j], xo[j] = in[2j+1].
 // A CTA de-interleaves its input span into xe / xo in shared memory; each thread produces 4 consecutive outputs
 // from a 67-sample register window (17 conflict-free LDS.128), float64 accumulation.
+// Accumulation type: float64 like the oracle.  A float32 variant (NCFA_DECIMATE=f32) was measured: 10.6 -> 8.3 ms per
+// 250 pairs only — the kernel is paced by its strided staging loads, not by the FP64 pipe — so the exact sums stay.
 constexpr int kDecOutPerCta = 1024;
+template <typename acc_t>
 __global__ void __launch_bounds__(256) decimate2_kernel(const float *__restrict__ audio,
                                                         const int64_t *__restrict__ seg_off,
                                                         const int32_t *__restrict__ seg_len, int level,
                                                         float *__restrict__ pyr, size_t pyr_stride, size_t in_off,
                                                         size_t out_off, const double *__restrict__ hb) {
-    __shared__ double h_even[64];
-    __shared__ double h_mid;
+    __shared__ acc_t h_even[64];
+    __shared__ acc_t h_mid;
     __shared__ __align__(16) float xo[kDecOutPerCta + 64 + 4];
     __shared__ __align__(16) float xe[kDecOutPerCta];
     const int seg = blockIdx.y;
@@ -483,8 +486,8 @@ __global__ void __launch_bounds__(256) decimate2_kernel(const float *__restrict_
     if (o0 >= n_out) return;
     const float *in = (level == 1) ? audio + seg_off[seg] : pyr + (size_t)seg * pyr_stride + in_off;
     float *out = pyr + (size_t)seg * pyr_stride + out_off;
-    if (threadIdx.x < 64) h_even[threadIdx.x] = hb[2 * threadIdx.x];
-    if (threadIdx.x == 64) h_mid = hb[(kHbTaps - 1) / 2];
+    if (threadIdx.x < 64) h_even[threadIdx.x] = (acc_t)hb[2 * threadIdx.x];
+    if (threadIdx.x == 64) h_mid = (acc_t)hb[(kHbTaps - 1) / 2];
     // xo[i] = in[2(o0 − 32 + i) + 1], i < 1024 + 64 + 4;  xe[i] = in[2(o0 + i)], i < 1024
     for (int i = threadIdx.x; i < kDecOutPerCta + 64 + 4; i += 256) {
         const int64_t p = 2 * ((int64_t)o0 - 32 + i) + 1;
@@ -506,20 +509,29 @@ __global__ void __launch_bounds__(256) decimate2_kernel(const float *__restrict_
         w[4 * j + 3] = v.w;
     }
     const float4 e = *reinterpret_cast<const float4 *>(xe + t);
-    double a0 = h_mid * (double)e.x, a1 = h_mid * (double)e.y, a2 = h_mid * (double)e.z, a3 = h_mid * (double)e.w;
+    acc_t a0 = h_mid * (acc_t)e.x, a1 = h_mid * (acc_t)e.y, a2 = h_mid * (acc_t)e.z, a3 = h_mid * (acc_t)e.w;
 #pragma unroll
     for (int m = 0; m < 64; ++m) {
-        const double hm = h_even[m];
-        a0 = fma(hm, (double)w[m], a0);
-        a1 = fma(hm, (double)w[m + 1], a1);
-        a2 = fma(hm, (double)w[m + 2], a2);
-        a3 = fma(hm, (double)w[m + 3], a3);
+        const acc_t hm = h_even[m];
+        a0 = fma(hm, (acc_t)w[m], a0);
+        a1 = fma(hm, (acc_t)w[m + 1], a1);
+        a2 = fma(hm, (acc_t)w[m + 2], a2);
+        a3 = fma(hm, (acc_t)w[m + 3], a3);
     }
+    const acc_t r2 = (acc_t)1.4142135623730951;
     const int o = o0 + t;
-    if (o < n_out) out[o] = (float)(a0 * 1.4142135623730951);
-    if (o + 1 < n_out) out[o + 1] = (float)(a1 * 1.4142135623730951);
-    if (o + 2 < n_out) out[o + 2] = (float)(a2 * 1.4142135623730951);
-    if (o + 3 < n_out) out[o + 3] = (float)(a3 * 1.4142135623730951);
+    if (o < n_out) out[o] = (float)(a0 * r2);
+    if (o + 1 < n_out) out[o + 1] = (float)(a1 * r2);
+    if (o + 2 < n_out) out[o + 2] = (float)(a2 * r2);
+    if (o + 3 < n_out) out[o + 3] = (float)(a3 * r2);
+}
+
+static bool decimate_f64() {
+    static const bool v = [] {
+        const char *e = getenv("NCFA_DECIMATE");
+        return !(e && strcmp(e, "f32") == 0);
+    }();
+    return v;
 }
 
 // ------------------------------------------------------------------------------------------------ CQT → chroma
@@ -1155,8 +1167,12 @@ extern "C" int ncfa_chroma_mean_batched(const float *d_audio, const int64_t *d_s
         if (n_out <= 0) continue;
         ProfScope _p("decimate2_kernel", st);
         dim3 g((n_out + kDecOutPerCta - 1) / kDecOutPerCta, n_seg);
-        decimate2_kernel<<<g, 256, 0, st>>>(d_audio, d_seg_off, d_seg_len, level, pyr, stride,
-                                            level >= 2 ? po.off[level - 1] : 0, po.off[level], ct.hb);
+        if (decimate_f64())
+            decimate2_kernel<double><<<g, 256, 0, st>>>(d_audio, d_seg_off, d_seg_len, level, pyr, stride,
+                                                        level >= 2 ? po.off[level - 1] : 0, po.off[level], ct.hb);
+        else
+            decimate2_kernel<float><<<g, 256, 0, st>>>(d_audio, d_seg_off, d_seg_len, level, pyr, stride,
+                                                       level >= 2 ? po.off[level - 1] : 0, po.off[level], ct.hb);
         NCFA_LAUNCH_OK("decimate2_kernel");
     }
     // NCFA_CQT_IMPL=simt selects the CUDA-core contraction (kept as the cross-check of the tensor-core kernel)
