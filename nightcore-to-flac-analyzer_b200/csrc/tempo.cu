@@ -202,7 +202,10 @@ __global__ void __launch_bounds__(kLagThreads) tg_lag_kernel(const float *__rest
                                                              const int2 *__restrict__ todo,
                                                              const int2 *__restrict__ done,
                                                              double *__restrict__ partial) {
-    extern __shared__ double xs[];  // chunk + W
+    // chunk + W padded-envelope samples.  They are float32 values (the onset envelope and the linear-ramp padding, which
+    // numpy computes in the envelope's dtype), so staging them as float loses nothing and halves the shared memory of a
+    // CTA: 7 instead of 4 CTAs per SM hide the FP64 latencies of the sliding update.
+    extern __shared__ float xs[];
     const int seg = blockIdx.z;
     const int n = env_len[seg];
     const int t0 = blockIdx.y * chunk;
@@ -221,7 +224,7 @@ __global__ void __launch_bounds__(kLagThreads) tg_lag_kernel(const float *__rest
     const int span = (t1 - t0) + W;  // x[t0 .. t1-1+W]
     for (int i = threadIdx.x; i < span; i += kLagThreads) {
         int m = t0 + i;
-        xs[i] = (m < n + 2 * p) ? padded_env(on, n, p, m) : 0.0;
+        xs[i] = (m < n + 2 * p) ? (float)padded_env(on, n, p, m) : 0.0f;
     }
     __syncthreads();
     const int k = kb + threadIdx.x;
@@ -241,11 +244,11 @@ __global__ void __launch_bounds__(kLagThreads) tg_lag_kernel(const float *__rest
     int t = t0;
     while (t < t1) {
         // ---- rebuild the three running sums at frame t
-        const double *xa = xs + (t - t0);
+        const float *xa = xs + (t - t0);
         double S0 = 0, S1r = 0, S1i = 0, S2r = 0, S2i = 0;
         for (int j = 0; j < Lmax; ++j) {
             if (j < L) {
-                const double z = xa[j] * xa[j + kk];
+                const double z = (double)xa[j] * (double)xa[j + kk];
                 const double2 a = trig[j];
                 int j2 = 2 * j;
                 if (j2 >= W) j2 -= W;
@@ -258,7 +261,7 @@ __global__ void __launch_bounds__(kLagThreads) tg_lag_kernel(const float *__rest
             }
         }
         double inv = fabs(ri[t]);
-        const double *xk = xa + kk, *xl = xa + L, *xw = xa + W;
+        const float *xk = xa + kk, *xl = xa + L, *xw = xa + W;
         const double *rn = ri + t + 1;
         double nx = *rn;  // one frame ahead (the entry after the last frame is never used, but it is inside the workspace)
         // ---- slide until the chunk ends or the next frame asks for a rebuild
@@ -270,8 +273,8 @@ __global__ void __launch_bounds__(kLagThreads) tg_lag_kernel(const float *__rest
             nx = *++rn;
             if (__double2hiint(cur) < 0) break;  // sign set (or a NaN with it): rebuild at t
             inv = cur;
-            const double zr = (*xa++) * (*xk++);
-            const double za = (*xl++) * (*xw++);
+            const double zr = (double)(*xa++) * (double)(*xk++);
+            const double za = (double)(*xl++) * (double)(*xw++);
             S0 = S0 - zr + za;
             const double a1 = fma(za, eL.x, S1r - zr), b1 = fma(za, eL.y, S1i);
             S1r = a1 * e1.x + b1 * e1.y;
@@ -505,7 +508,7 @@ extern "C" int ncfa_tempo_lag_batched(const float *d_onset, const int64_t *d_ons
     }
     NCFA_LAUNCH_OK("tg_range_kernel");
     {
-        size_t sh = (size_t)(chunk + W) * 8;
+        size_t sh = (size_t)(chunk + W) * 4;
         if (sh > 48 * 1024) {
             int rc = ensure_dynamic_smem((const void *)tg_lag_kernel, sh);
             if (rc) return rc;
