@@ -230,7 +230,8 @@ __global__ void __launch_bounds__(kLagThreads) tg_lag_kernel(const float *__rest
     const int k = kb + threadIdx.x;
     const bool active = k < td.y && k < W && !(k >= dn.x && k < dn.y);
     if (!__any_sync(0xffffffffu, active)) return;
-    const int kk = active ? k : W - 1;
+    // lanes without a live lag shadow the warp's first lag (live warps have kw < W): same trip counts, in-bounds reads
+    const int kk = active ? k : kb + (int)(threadIdx.x & ~31u);
     const int L = W - kk;
     const double2 ek = trig[kk];
     const double2 e1 = trig[1 % W], e2 = trig[2 % W];
@@ -246,20 +247,25 @@ __global__ void __launch_bounds__(kLagThreads) tg_lag_kernel(const float *__rest
         // ---- rebuild the three running sums at frame t
         const float *xa = xs + (t - t0);
         double S0 = 0, S1r = 0, S1i = 0, S2r = 0, S2i = 0;
-        for (int j = 0; j < Lmax; ++j) {
-            if (j < L) {
-                const double z = (double)xa[j] * (double)xa[j + kk];
-                const double2 a = trig[j];
-                int j2 = 2 * j;
-                if (j2 >= W) j2 -= W;
-                const double2 b = trig[j2];
-                S0 += z;
-                S1r = fma(z, a.x, S1r);
-                S1i = fma(z, a.y, S1i);
-                S2r = fma(z, b.x, S2r);
-                S2i = fma(z, b.y, S2i);
-            }
-        }
+        auto term = [&](int j) {
+            const double z = (double)xa[j] * (double)xa[j + kk];
+            const double2 a = trig[j];
+            int j2 = 2 * j;
+            if (j2 >= W) j2 -= W;
+            const double2 b = trig[j2];
+            S0 += z;
+            S1r = fma(z, a.x, S1r);
+            S1i = fma(z, a.y, S1i);
+            S2r = fma(z, b.x, S2r);
+            S2i = fma(z, b.y, S2i);
+        };
+        // every lane of the warp has L >= Lmax - 31: that part needs no predicate, so its table loads can be batched
+        const int Lcommon = Lmax > 31 ? Lmax - 31 : 0;
+        int j = 0;
+#pragma unroll 4
+        for (; j < Lcommon; ++j) term(j);
+        for (; j < Lmax; ++j)
+            if (j < L) term(j);
         double inv = fabs(ri[t]);
         const float *xk = xa + kk, *xl = xa + L, *xw = xa + W;
         const double *rn = ri + t + 1;
