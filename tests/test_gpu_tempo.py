@@ -105,6 +105,38 @@ def test_tempo_lag_hop64(engine):
     assert got.tolist() == [lr.tempo_lag(env, SR, 64, 120.0)]
 
 
+def test_tempo_lag_weak_periodicity_and_off_centre_priors(engine):
+    """Noise envelopes have a flat tempogram, so the branch-and-bound cannot prune: phase 2 has to evaluate the lags on
+    BOTH sides of the phase-1 interval (exact, not block-aligned, intervals; ragged envelope lengths; priors far from
+    the data).  The argmax must still be the oracle's."""
+    rng = np.random.default_rng(77)
+    envs, priors = [], []
+    for n, p in ((431, 60.0), (431, 240.0), (300, 120.0), (97, 120.0), (431, 31.0), (1000, 300.0)):
+        e = rng.exponential(1.0, n).astype(np.float32)
+        e[:3] = 0.0
+        envs.append(e)
+        priors.append(p)
+    got = engine.tempo_lags(envs, priors, hop=512, sr=SR)
+    want = [lr.tempo_lag(e, SR, 512, p) for e, p in zip(envs, priors)]
+    assert got.tolist() == want
+    # hop 64: several 4096-frame chunks (ragged last chunk), weak periodicity, prior an octave off
+    e = (rng.exponential(1.0, 9000) * (1.0 + 0.3 * np.sin(np.arange(9000) * 2 * np.pi / 171.0))).astype(np.float32)
+    for p in (120.0, 55.0, 250.0):
+        assert engine.tempo_lags([e], [p], hop=64, sr=SR).tolist() == [lr.tempo_lag(e, SR, 64, p)]
+
+
+def test_tempo_lag_envelope_with_silent_stretches(engine):
+    """Frames whose energy collapses force the running sums to be rebuilt (sign flag of the stored reciprocal) and
+    all-zero stretches take the 'unscaled' branch of normalize(): the scores must survive both."""
+    y = synth.synth(21, 40.0, SR, bpm=117.0).copy()
+    y[5 * SR:12 * SR] = 0.0
+    y[20 * SR:21 * SR] *= 1e-4
+    env = lr.onset_strength(y, SR, 64)
+    assert engine.tempo_lags([env], [120.0], hop=64, sr=SR).tolist() == [lr.tempo_lag(env, SR, 64, 120.0)]
+    env512 = lr.onset_strength(y[: 10 * SR], SR, 512)
+    assert engine.tempo_lags([env512], [120.0], hop=512, sr=SR).tolist() == [lr.tempo_lag(env512, SR, 512, 120.0)]
+
+
 def test_tempo_lag_all_zero_envelope(engine):
     got = engine.tempo_lags([np.zeros(431, np.float32)], [120.0], hop=512, sr=SR)
     assert got.tolist() == [0]
@@ -127,6 +159,24 @@ def test_beat_frames_hop64(engine):
     got = engine.beat_frames([env], [lag], hop=64, sr=SR)[0]
     want = lr.beat_track_frames(env, 60.0 * SR / (64 * float(lag)), SR, 64)
     assert got.tolist() == want.tolist()
+
+
+def test_beat_frames_ragged_batch_and_slow_tempo(engine):
+    """One launch with envelopes of very different lengths and frames-per-beat (the local-score kernel's sliding
+    window needs full-width interiors; short envelopes and the ends take the one-frame path; a slow tempo makes the
+    DP ring wrap many times)."""
+    rng = np.random.default_rng(5)
+    envs, lags = [], []
+    for seed, dur, bpm in ((31, 12.0, 72.0), (32, 3.0, 160.0), (33, 25.0, 95.0)):
+        y = synth.synth(seed, dur, SR, bpm=bpm)
+        envs.append(lr.onset_strength(y, SR, 64))
+        lags.append(lr.tempo_lag(envs[-1], SR, 64, 120.0))
+    envs.append(rng.exponential(1.0, 700).astype(np.float32))
+    lags.append(400)   # window wider than the envelope: every frame is an edge frame
+    got = engine.beat_frames(envs, lags, hop=64, sr=SR)
+    for e, lag, g in zip(envs, lags, got):
+        want = lr.beat_track_frames(e, 60.0 * SR / (64 * float(lag)), SR, 64)
+        assert g.tolist() == want.tolist()
 
 
 def test_end_to_end_tempo_api(engine, windows):
