@@ -488,14 +488,26 @@ __global__ void __launch_bounds__(256) decimate2_kernel(const float *__restrict_
     float *out = pyr + (size_t)seg * pyr_stride + out_off;
     if (threadIdx.x < 64) h_even[threadIdx.x] = (acc_t)hb[2 * threadIdx.x];
     if (threadIdx.x == 64) h_mid = (acc_t)hb[(kHbTaps - 1) / 2];
-    // xo[i] = in[2(o0 − 32 + i) + 1], i < 1024 + 64 + 4;  xe[i] = in[2(o0 + i)], i < 1024
-    for (int i = threadIdx.x; i < kDecOutPerCta + 64 + 4; i += 256) {
-        const int64_t p = 2 * ((int64_t)o0 - 32 + i) + 1;
-        xo[i] = (p >= 0 && p < n_in) ? __ldg(in + p) : 0.0f;
-    }
-    for (int i = threadIdx.x; i < kDecOutPerCta; i += 256) {
-        const int64_t p = 2 * ((int64_t)o0 + i);
-        xe[i] = (p < n_in) ? __ldg(in + p) : 0.0f;
+    // xo[i] = in[2(o0 − 32 + i) + 1], i < 1024 + 64 + 4;  xe[i] = in[2(o0 + i)], i < 1024: one coalesced float2 load
+    // (even sample, odd sample) feeds both arrays when the level's base is 8-byte aligned
+    if ((reinterpret_cast<uintptr_t>(in) & 7u) == 0) {
+        for (int i = threadIdx.x; i < kDecOutPerCta + 64 + 4; i += 256) {
+            const int64_t p = 2 * ((int64_t)o0 - 32 + i);
+            float2 v = make_float2(0.0f, 0.0f);
+            if (p >= 0 && p + 1 < n_in) v = __ldg(reinterpret_cast<const float2 *>(in + p));
+            else if (p >= 0 && p < n_in) v.x = __ldg(in + p);
+            xo[i] = v.y;
+            if (i >= 32 && i < 32 + kDecOutPerCta) xe[i - 32] = v.x;
+        }
+    } else {
+        for (int i = threadIdx.x; i < kDecOutPerCta + 64 + 4; i += 256) {
+            const int64_t p = 2 * ((int64_t)o0 - 32 + i) + 1;
+            xo[i] = (p >= 0 && p < n_in) ? __ldg(in + p) : 0.0f;
+        }
+        for (int i = threadIdx.x; i < kDecOutPerCta; i += 256) {
+            const int64_t p = 2 * ((int64_t)o0 + i);
+            xe[i] = (p < n_in) ? __ldg(in + p) : 0.0f;
+        }
     }
     __syncthreads();
     const int t = 4 * threadIdx.x;  // outputs o0 + t .. o0 + t + 3 use xo[t .. t + 66]
@@ -520,10 +532,15 @@ __global__ void __launch_bounds__(256) decimate2_kernel(const float *__restrict_
     }
     const acc_t r2 = (acc_t)1.4142135623730951;
     const int o = o0 + t;
-    if (o < n_out) out[o] = (float)(a0 * r2);
-    if (o + 1 < n_out) out[o + 1] = (float)(a1 * r2);
-    if (o + 2 < n_out) out[o + 2] = (float)(a2 * r2);
-    if (o + 3 < n_out) out[o + 3] = (float)(a3 * r2);
+    if (o + 3 < n_out && (reinterpret_cast<uintptr_t>(out + o) & 15u) == 0) {  // level offsets are multiples of 4 floats
+        *reinterpret_cast<float4 *>(out + o) =
+            make_float4((float)(a0 * r2), (float)(a1 * r2), (float)(a2 * r2), (float)(a3 * r2));
+    } else {
+        if (o < n_out) out[o] = (float)(a0 * r2);
+        if (o + 1 < n_out) out[o + 1] = (float)(a1 * r2);
+        if (o + 2 < n_out) out[o + 2] = (float)(a2 * r2);
+        if (o + 3 < n_out) out[o + 3] = (float)(a3 * r2);
+    }
 }
 
 static bool decimate_f64() {
