@@ -86,6 +86,9 @@ __global__ void __launch_bounds__(kThreads, 1) stft_logmel_kernel(const float *_
 }
 
 // onset[j] = 0 for j < pad;  else mean_m relu(clamp(S[j-pad+1][m]) - clamp(S[j-pad][m]))
+// A warp walks kFluxRun consecutive frames and keeps the previous log-mel row in registers, so every row is read from
+// L2 once (the kernel is L2-bandwidth bound: 512 B per frame).  Per frame: 4 bands per lane, then the xor tree.
+constexpr int kFluxRun = 8;
 __global__ void __launch_bounds__(256) flux_kernel(const float *__restrict__ S, const unsigned *__restrict__ seg_max,
                                                    const int32_t *__restrict__ seg_len, int hop, int frame_stride,
                                                    int pad, float *__restrict__ onset,
@@ -93,23 +96,35 @@ __global__ void __launch_bounds__(256) flux_kernel(const float *__restrict__ S, 
     const int seg = blockIdx.y;
     const int n_frames = 1 + seg_len[seg] / hop;
     const int lane = threadIdx.x & 31;
-    const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (j >= n_frames) return;
+    const int j0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * kFluxRun;
+    if (j0 >= n_frames) return;
     float *out = onset + onset_off[seg];
-    if (j < pad) {
-        if (lane == 0) out[j] = 0.0f;
-        return;
-    }
     const float floor_db = ordered_to_float(seg_max[seg]) - 80.0f;
-    const float4 *row0 = reinterpret_cast<const float4 *>(S + ((size_t)seg * frame_stride + (j - pad)) * NCFA_N_MELS);
-    const float4 *row1 = row0 + NCFA_N_MELS / 4;
-    float4 a = row0[lane], b = row1[lane];
-    float s = fmaxf(0.0f, fmaxf(b.x, floor_db) - fmaxf(a.x, floor_db));
-    s += fmaxf(0.0f, fmaxf(b.y, floor_db) - fmaxf(a.y, floor_db));
-    s += fmaxf(0.0f, fmaxf(b.z, floor_db) - fmaxf(a.z, floor_db));
-    s += fmaxf(0.0f, fmaxf(b.w, floor_db) - fmaxf(a.w, floor_db));
-    s = warp_sum(s);
-    if (lane == 0) out[j] = s * (1.0f / NCFA_N_MELS);
+    const float4 *rows = reinterpret_cast<const float4 *>(S + (size_t)seg * frame_stride * NCFA_N_MELS);
+    const int j1 = min(n_frames, j0 + kFluxRun);
+    int j = j0;
+    for (; j < j1 && j < pad; ++j)
+        if (lane == 0) out[j] = 0.0f;
+    if (j >= j1) return;
+    float4 a = rows[(size_t)(j - pad) * (NCFA_N_MELS / 4) + lane];
+    a.x = fmaxf(a.x, floor_db);
+    a.y = fmaxf(a.y, floor_db);
+    a.z = fmaxf(a.z, floor_db);
+    a.w = fmaxf(a.w, floor_db);
+    for (; j < j1; ++j) {
+        float4 b = rows[(size_t)(j - pad + 1) * (NCFA_N_MELS / 4) + lane];
+        b.x = fmaxf(b.x, floor_db);
+        b.y = fmaxf(b.y, floor_db);
+        b.z = fmaxf(b.z, floor_db);
+        b.w = fmaxf(b.w, floor_db);
+        float s = fmaxf(0.0f, b.x - a.x);
+        s += fmaxf(0.0f, b.y - a.y);
+        s += fmaxf(0.0f, b.z - a.z);
+        s += fmaxf(0.0f, b.w - a.w);
+        s = warp_sum(s);
+        if (lane == 0) out[j] = s * (1.0f / NCFA_N_MELS);
+        a = b;
+    }
 }
 
 // ---- tile form (cross-check) ------------------------------------------------------------------------------------------
@@ -316,7 +331,7 @@ extern "C" int ncfa_onset_strength_batched(const float *d_audio, const int64_t *
     }
     NCFA_LAUNCH_OK("stft_logmel_kernel");
     const int pad = 1 + NCFA_N_FFT / (2 * hop);
-    dim3 g2((frames + 7) / 8, n_seg);
+    dim3 g2((frames + 8 * kFluxRun - 1) / (8 * kFluxRun), n_seg);
     {
         ProfScope _p("flux_kernel", st);
         flux_kernel<<<g2, 256, 0, st>>>(S, seg_max, d_seg_len, hop, frames, pad, d_onset, d_onset_off);
