@@ -228,7 +228,7 @@ int get_tables(int sr, Tables *out) {
         return NCFA_OK;
     }
     NCFA_REQUIRE(sr >= 2000 && sr <= 768000, "sample rate out of range");
-    const int n_fft = NCFA_N_FFT, n_mels = NCFA_N_MELS, n_bins = n_fft / 2 + 1;
+    const int n_fft = NCFA_N_FFT, n_mels = NCFA_N_MELS;
     const double PI = 3.14159265358979323846;
     std::vector<float> hann(n_fft);
     for (int i = 0; i < n_fft; ++i) hann[i] = (float)(0.5 - 0.5 * cos(2.0 * PI * i / n_fft));
