@@ -84,6 +84,32 @@ def test_stft_against_torch():
     assert np.max(np.abs(D - T)) < 1e-3 * np.max(np.abs(T))
 
 
+def test_logmel_db_against_torchaudio():
+    """The front half of onset_strength (melspectrogram(power=2) -> power_to_db(top_db=80)) against torchaudio's
+    independent implementation of the same librosa semantics (MelSpectrogram with Slaney scale/norm, zero-padded
+    centred frames, AmplitudeToDB('power', top_db=80)) on synthetic music, at both hops the path uses."""
+    import torch
+    try:
+        import torchaudio
+    except Exception:
+        pytest.skip("torchaudio not installed")
+    from oracle import synth
+    y = synth.synth(17, 4.0, 22050, bpm=124.0)
+    for hop in (512, 64):
+        mel = torchaudio.transforms.MelSpectrogram(sample_rate=22050, n_fft=2048, hop_length=hop, f_min=0.0, f_max=11025.0,
+                                                   n_mels=128, power=2.0, center=True, pad_mode="constant", norm="slaney",
+                                                   mel_scale="slaney").double()
+        S = mel(torch.from_numpy(y).double())
+        want = torchaudio.transforms.AmplitudeToDB(stype="power", top_db=80.0)(S).numpy()
+        got = lr.logmel_db(y, 22050, hop)
+        assert got.shape == want.shape == (128, 1 + len(y) // hop)
+        assert np.max(np.abs(got - want)) < 2e-3          # dB; float32 mel bank on one side, float64 on the other
+        # and the flux built on it (the onset envelope itself) agrees to 1e-4 of its maximum
+        env_t = lr.onset_from_logmel(want.astype(np.float32), 2048, hop)
+        env_o = lr.onset_strength(y, 22050, hop)
+        assert np.max(np.abs(env_t - env_o)) < 1e-4 * float(env_o.max())
+
+
 def test_onset_shape_and_padding():
     from oracle import synth
     y = synth.synth(11, 10.0, 22050, bpm=120.0)
