@@ -253,9 +253,10 @@ __global__ void __launch_bounds__(128) flux_tile_kernel(const float *__restrict_
     out[j] = q[0] * (1.0f / NCFA_N_MELS);
 }
 
-// measured on B200 (profiles/r1ai): the tile form is 7 % (hop 64) to 19 % (hop 512) SLOWER than the warp form — fewer
-// resident warps, two block barriers per tile and four shared round trips per transpose cost more than the mel phase
-// saves — so the warp form stays the default and the tile form is kept as a cross-check (NCFA_STFT_IMPL=tile).
+// measured on B200: the tile form was 7 % (hop 64) to 19 % (hop 512) SLOWER than the warp form when both were scalar
+// (profiles r1ai), and it gained nothing from the packed-FP32 FFT that sped the warp form up (109 vs 78 ms per 250 pairs,
+// r1bj): with 16 warps, two block barriers per tile and four shared round trips per transpose it is latency bound, not
+// issue bound.  The warp form stays the default; the tile form is kept as a cross-check (NCFA_STFT_IMPL=tile).
 static bool use_warp_form() {
     static const bool v = [] {
         const char *e = getenv("NCFA_STFT_IMPL");
