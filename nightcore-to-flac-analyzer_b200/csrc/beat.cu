@@ -141,6 +141,17 @@ __global__ void __launch_bounds__(256) beat_score_kernel(const int32_t *__restri
     const double *onorm = base, *window = base + 3 * (size_t)env_stride;
     double *ls = base + env_stride;
     const int Kw = 2 * fpb + 1;
+    // the CTA's slice of the normalised onsets, onorm[i0 − fpb … i0 + 1023 + fpb], staged in shared memory with a skewed
+    // index (e + e/16): lanes read elements 4 apart, which would otherwise be a 4-way bank conflict — and, from global
+    // memory, 32 sectors per load instruction (the LSU queue was the top stall of this kernel, profiles r1bl)
+    extern __shared__ double tile[];
+    const int lo_idx = i0 - fpb;
+    const int span = min(256 * kScoreFramesPerThread, N - i0) + 2 * fpb + 1;
+    for (int e = threadIdx.x; e < span; e += 256) {
+        const int idx = lo_idx + e;
+        tile[e + (e >> 4)] = (idx >= 0 && idx < N) ? onorm[idx] : 0.0;
+    }
+    __syncthreads();
     double lmax = -INFINITY;
     // a thread owns kScoreFramesPerThread CONSECUTIVE frames: away from the envelope's ends all of them run over the
     // full window, so one window load and one new onset load feed four multiply-adds (register sliding window); every
@@ -149,8 +160,9 @@ __global__ void __launch_bounds__(256) beat_score_kernel(const int32_t *__restri
     if (ib < N) {
         if (ib + fpb >= Kw && ib + kScoreFramesPerThread - 1 + fpb - N + 1 <= 0) {
             // acc_r = Σ_k window[k]·onorm[ib + r + fpb − k]: with x_j = onorm[ib + fpb − k + j], step k → k+1 shifts x down
-            const double *xo = onorm + ib + fpb;
-            double x0 = xo[0], x1 = xo[1], x2 = xo[2], x3 = xo[3];
+            const int e0 = (ib - i0) + 2 * fpb;  // tile index of onorm[ib + fpb]
+            auto T = [&](int e) { return tile[e + (e >> 4)]; };
+            double x0 = T(e0), x1 = T(e0 + 1), x2 = T(e0 + 2), x3 = T(e0 + 3);
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             for (int k = 0; k < Kw; ++k) {
                 const double w = window[k];
@@ -161,7 +173,8 @@ __global__ void __launch_bounds__(256) beat_score_kernel(const int32_t *__restri
                 x3 = x2;
                 x2 = x1;
                 x1 = x0;
-                x0 = xo[-(k + 1)];
+                const int en = e0 - (k + 1);  // −1 after the last tap of the tile's first frame: that value is never used
+                x0 = T(en < 0 ? 0 : en);
             }
             ls[ib] = a0;
             ls[ib + 1] = a1;
@@ -415,7 +428,11 @@ extern "C" int ncfa_beat_track_batched(const float *d_onset, const int64_t *d_on
         dim3 g(n_seg, (max_env_len + 256 * kScoreFramesPerThread - 1) / (256 * kScoreFramesPerThread));
         NCFA_REQUIRE(g.y <= 65535, "envelope too long for one call");
         ProfScope _p("beat_score_kernel", (cudaStream_t)stream);
-        beat_score_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(d_env_len, max_env_len, d_lag, wf, max_lag);
+        const size_t tile_elems = (size_t)256 * kScoreFramesPerThread + 2 * (size_t)max_lag + 1;
+        const size_t smem_score = (tile_elems + tile_elems / 16 + 2) * sizeof(double);
+        int rcs = ensure_dynamic_smem((const void *)beat_score_kernel, smem_score);
+        if (rcs) return rcs;
+        beat_score_kernel<<<g, 256, smem_score, (cudaStream_t)stream>>>(d_env_len, max_env_len, d_lag, wf, max_lag);
     }
     NCFA_LAUNCH_OK("beat_score_kernel");
     {
