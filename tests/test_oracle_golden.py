@@ -132,3 +132,29 @@ def test_tempo_and_beats_on_click_track():
     assert len(beats) >= 15
     d = np.diff(beats)
     assert abs(np.median(d) - 60.0 * 22050 / 512 / 120.0) <= 1.0
+
+
+def test_tempogram_against_its_definition_and_the_sliding_sum_identity():
+    """(1) The FFT-route tempogram of the restatement equals the direct definition
+    R_t[k] = sum_j w[j] w[j+k] x[t+j] x[t+j+k] / max_k R_t[k] on a small case.  (2) The identity behind the CUDA
+    kernel (tempo.cu): with w the periodic Hann window, w[j]·w[j+k] is a three-term trigonometric polynomial in j, so
+    R_t[k] = 1/4 [(1 + c/2) S0 - (1 + c) Re S1 + s Im S1 + c/2 Re S2 - s/2 Im S2] with S_m = sum_{j<W-k} z_j e^{i m theta j},
+    z_j = x[t+j] x[t+j+k], theta = 2 pi / W, c = cos(theta k), s = sin(theta k)."""
+    rng = np.random.default_rng(9)
+    W = 48
+    env = rng.exponential(1.0, 200).astype(np.float32)
+    tg = lr.tempogram(env, W)
+    x = lr.tempogram_frames(env, W).astype(np.float64)
+    w = lr.hann_periodic(W)
+    theta = 2.0 * np.pi / W
+    for t in (0, 7, 101, 199):
+        direct = np.array([np.sum(w[: W - k] * w[k:] * x[t : t + W - k] * x[t + k : t + W]) for k in range(W)])
+        want = direct / np.max(np.abs(direct))
+        assert np.max(np.abs(tg[:, t] - want)) < 1e-12
+        for k in (1, 5, 17, 40):
+            j = np.arange(W - k)
+            z = x[t + j] * x[t + j + k]
+            S0, S1, S2 = z.sum(), np.sum(z * np.exp(1j * theta * j)), np.sum(z * np.exp(2j * theta * j))
+            c, s_ = np.cos(theta * k), np.sin(theta * k)
+            R = 0.25 * ((1 + 0.5 * c) * S0 - (1 + c) * S1.real + s_ * S1.imag + 0.5 * c * S2.real - 0.5 * s_ * S2.imag)
+            assert abs(R - direct[k]) < 1e-12 * max(1.0, abs(direct[k]))
