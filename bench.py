@@ -2,14 +2,22 @@
 """Benchmark of the windowed spectral front-end on B200 (BASELINE.json metric: analysis windows/sec
 and track-pairs/sec).
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --steps K --warmup W    # the CPU path on the host cores
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (config 5, the contract line)
+    python bench.py --impl reference --steps K --warmup W    # the CPU path on the host cores, same config
+    python bench.py --config 2|3|4 [--steps K]               # per-family lines of BASELINE configs 2 / 3 / 4
+    python bench.py --single-pair                            # config 1: latency of one pair
 
 A step = one full analysis (strip → slice → gate → pitch → tempo src → prior → tempo nc → hop-64
 IBI pass → bootstraps → result assembly) of a batch of synthetic track pairs of BASELINE config 5
-(180 s source at 22 050 Hz + 1.25× nightcore).  `value` is measured with the batch resident in HBM;
-`e2e` goes through the public batch API with host buffers (pinned → H2D inside the timed region,
-results back on the host).  One JSON line on stdout (rank 0).
+(180 s source at 22 050 Hz + 1.25× nightcore; 32 distinct pairs tiled to the batch size).
+`value` is measured with the batch resident in HBM; `e2e` goes through the public batch API
+(`nightcore_analyzer.run_batch`) with the batch in pinned host memory (H2D inside the timed region,
+results back on the host); `e2e_pageable` starts from ordinary numpy arrays.  One JSON line on stdout (rank 0).
+
+The reference arm times the CPU port of the reference's pipeline (oracle/pipeline_port.py — the reference
+itself needs librosa and does not exist on the GPU box) on the SAME configuration: 180 s pairs, all host
+cores, a bounded sample of pairs per step, its independent units (windows, chunks, whole-track passes) dealt
+to one process per core (oracle/pipeline_tasks.py).
 """
 from __future__ import annotations
 
@@ -29,7 +37,18 @@ import numpy as np  # noqa: E402
 
 SR = 22050
 PAIR_SEC = 180.0
-N_DISTINCT = 8          # distinct synthetic pairs, tiled to the batch size (stated in `data`)
+N_DISTINCT = 32          # distinct synthetic pairs, tiled to the batch size (stated in `data`)
+NC_SEC_PER_SRC_SEC = 0.8  # nightcore = resample_poly(src, 4, 5)
+
+WORKLOAD = ("config 5: batch of 1000 synthetic 180 s track pairs (22050 Hz source + 1.25x nightcore), "
+            "full windowed tempo+pitch+IBI+bootstrap analysis, pairs sharded across ranks")
+
+
+def workload_config(pairs: int, pair_sec: float) -> dict:
+    """The workload description — identical in the GPU arm and the reference arm."""
+    gb = pairs * pair_sec * (1.0 + NC_SEC_PER_SRC_SEC) * SR * 4 / 1e9
+    return {"workload": WORKLOAD, "pairs": pairs, "pair_sec": pair_sec, "sr": SR, "n_distinct": N_DISTINCT,
+            "l2": f"inputs larger than L2: {gb:.1f} GB of audio per step, every sample read from HBM (126 MB L2)"}
 
 
 def load_peaks():
@@ -51,13 +70,24 @@ def load_traffic(kernel: str):
         return None, None
 
 
-def make_pairs(n_distinct: int, dur: float):
+def _synth_pair(args):
+    i, dur = args
     from oracle import synth
-    pairs = []
-    for i in range(n_distinct):
-        src, nc = synth.make_pair(5000 + i, dur, SR)
-        pairs.append((nc, src))
-    return pairs
+    src, nc = synth.make_pair(5000 + i, dur, SR)
+    return i, nc, src
+
+
+def make_pairs(ids, dur: float, procs: int = 0) -> dict:
+    """{i: (nc, src)} for the distinct pair indices `ids` (oracle/synth.py, seeds 5000 + i), synthesised in parallel."""
+    import multiprocessing as mp
+    ids = sorted(set(int(i) for i in ids))
+    procs = max(1, min(len(ids), procs or (os.cpu_count() or 1)))
+    if procs == 1:
+        out = [_synth_pair((i, dur)) for i in ids]
+    else:
+        with mp.get_context("fork").Pool(procs) as pool:
+            out = pool.map(_synth_pair, [(i, dur) for i in ids], chunksize=1)
+    return {i: (nc, src) for i, nc, src in out}
 
 
 class ClockSampler:
@@ -104,39 +134,43 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------- CPU arm
-def _cpu_one_pair(args):
-    """One pair through the CPU port in a worker process.  BLAS/OpenMP pools are pinned to one thread so that P
-    processes use P cores (without this the einsum/BLAS pools oversubscribe the box and the baseline is ~3x slower)."""
-    nc, src = args
-    from oracle import pipeline_port
-    try:
-        from threadpoolctl import threadpool_limits
-    except Exception:  # pragma: no cover
-        threadpool_limits = None
-    t0 = time.perf_counter()
-    if threadpool_limits is not None:
-        with threadpool_limits(limits=1):
-            res, n_windows = pipeline_port.run_arrays(nc, src, SR, log=None, return_window_count=True)
-    else:
-        res, n_windows = pipeline_port.run_arrays(nc, src, SR, log=None, return_window_count=True)
-    return n_windows, time.perf_counter() - t0
+class CpuArm:
+    """The CPU port on `procs` host processes: a step analyses a sample of `n_sample` pairs of `dur` seconds, their
+    independent units dealt to the pool (oracle/pipeline_tasks.py)."""
+
+    def __init__(self, dur: float, procs: int, n_sample: int, pairs: dict = None):
+        from oracle import pipeline_tasks
+        self.procs, self.n, self.dur = procs, max(1, n_sample), dur
+        n_distinct = min(N_DISTINCT, 2 * self.n)
+        if pairs is None or any(i not in pairs for i in range(n_distinct)):
+            pairs = make_pairs(range(n_distinct), dur, procs)
+        self.pairs = [pairs[i] for i in range(n_distinct)]
+        self.runner = pipeline_tasks.TaskRunner(self.pairs, SR, procs=procs, faithful_cost=True)
+        self.cursor = 0
+
+    def step(self, n=None):
+        n = self.n if n is None else n
+        ids = [(self.cursor + j) % len(self.pairs) for j in range(n)]
+        self.cursor += n
+        t0 = time.perf_counter()
+        results, windows = self.runner.run(ids)
+        wall = time.perf_counter() - t0
+        bad = [r for r in results if isinstance(r, Exception)]
+        if bad:
+            raise bad[0]
+        return windows, n, wall
+
+    def sample_text(self):
+        return (f"{self.n} pairs of {self.dur:.0f} s source + 1.25x nightcore per step (config 5 shape: 35 + 27 windows, "
+                f"7 chunk pairs, 2 hop-64 whole-track passes per pair), units dealt to {self.procs} processes; "
+                f"throughput extrapolates linearly to the 1000-pair batch")
+
+    def close(self):
+        self.runner.close()
 
 
-def cpu_throughput(n_pairs: int, dur: float, procs: int):
-    """windows/s and pairs/s of the CPU restatement (oracle port) on `procs` host processes."""
-    import multiprocessing as mp
-    pairs = make_pairs(min(n_pairs, N_DISTINCT), dur)
-    work = [pairs[i % len(pairs)] for i in range(n_pairs)]
-    ctx = mp.get_context("fork")
-    t0 = time.perf_counter()
-    if procs > 1:
-        with ctx.Pool(procs) as pool:
-            out = pool.map(_cpu_one_pair, work, chunksize=1)
-    else:
-        out = [_cpu_one_pair(w) for w in work]
-    wall = time.perf_counter() - t0
-    windows = sum(o[0] for o in out)
-    return windows / wall, n_pairs / wall, wall, windows
+def audio_seconds(n_pairs: float, pair_sec: float) -> float:
+    return n_pairs * pair_sec * (1.0 + NC_SEC_PER_SRC_SEC)
 
 
 def run_reference(args):
@@ -145,32 +179,33 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, args.cpu_procs or cores))
-    n_pairs = procs
-    dur = args.cpu_dur
+    arm = CpuArm(args.pair_sec, procs, args.cpu_sample or max(1, procs // 4))
     vals, pps, walls = [], [], []
-    for s in range(args.warmup + args.steps):
-        w, p, wall, nwin = cpu_throughput(n_pairs, dur, procs)
-        if s >= args.warmup:
-            vals.append(w)
-            pps.append(p)
+    try:
+        for s in range(args.warmup):
+            arm.step(1)                       # warm-up on a one-pair sample (page cache, FFT plans, BLAS pools)
+        for s in range(args.steps):
+            w, n, wall = arm.step()
+            vals.append(w / wall)
+            pps.append(n / wall)
             walls.append(wall)
-    v = float(np.mean(vals))
-    sample = f"{n_pairs} pairs of {dur:.0f}s source + 1.25x nightcore per step, one pair per process"
+    finally:
+        arm.close()
+    v = float(np.sum([a * b for a, b in zip(vals, walls)]) / np.sum(walls))      # windows of all steps / time of all steps
+    p = float(len(walls) * arm.n / np.sum(walls))
     line = {
         "impl": "reference", "metric": "analysis_windows_per_sec", "value": v, "unit": "windows/s",
-        "pairs_per_sec": float(np.mean(pps)), "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "pairs_per_sec": p, "audio_sec_per_sec": audio_seconds(p, args.pair_sec), "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * float(np.mean(walls)), "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "pairs": n_pairs, "pair_sec": dur, "sr": SR},
-        "cpu_baseline": {"value": v, "unit": "windows/s", "cores": procs, "kind": "port", "sample": sample},
+        "vs_baseline": None, "dtype": "f32", "data": f"synthetic ({N_DISTINCT} distinct pairs; oracle/synth.py)",
+        "config": workload_config(args.pairs, args.pair_sec),
+        "cpu_baseline": {"value": v, "unit": "windows/s", "cores": procs, "kind": "port", "sample": arm.sample_text(),
+                         "pairs_per_sec": p, "warmup_sample": "1 pair per warm-up step"},
         "e2e": {"value": v, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
-
-
-WORKLOAD = ("config 5: batch of 1000 synthetic 180 s track pairs (22050 Hz source + 1.25x nightcore), "
-            "full windowed tempo+pitch+IBI+bootstrap analysis, pairs sharded across ranks")
 
 
 # --------------------------------------------------------------------------------------- GPU arm
@@ -186,46 +221,46 @@ def run_gpu(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    from nightcore_analyzer import _engine, batch as nbatch, parallel as npar
+    import nightcore_analyzer as na
+    from nightcore_analyzer import _engine, _native, batch as nbatch, parallel as npar
 
     eng = _engine.get_engine()
     total_pairs = args.pairs
     my_ids = npar.shard_indices(total_pairs, rank, world)
-    distinct = make_pairs(min(N_DISTINCT, max(1, total_pairs)), args.pair_sec)
+    n_distinct = min(N_DISTINCT, max(1, total_pairs))
+    cores = os.cpu_count() or 1
+    need = set(i % n_distinct for i in my_ids) | (set(range(n_distinct)) if rank == 0 else set())
+    distinct = make_pairs(need, args.pair_sec, max(1, cores // world))
+    pairs_np = [distinct[i % n_distinct] for i in my_ids]          # ordinary (pageable) numpy arrays
     kw = dict(compute_pitch=not args.no_pitch, compute_ibi=not args.no_ibi)
 
-    # The rank's pairs are analysed in sub-batches (the batch scheduler of DESIGN.md): every sub-batch has the
-    # same composition (distinct pairs tiled), so ONE pinned host buffer feeds all of them.
-    sub = max(1, min(args.sub_batch, len(my_ids))) if my_ids else 1
-    sizes = [min(sub, len(my_ids) - s) for s in range(0, len(my_ids), sub)]        # resident sub-batches
-    sub_e2e = min(sub, max(16, -(-len(my_ids) // 4)))                            # at least ~4 pieces per rank
-    sizes_e2e = nbatch.plan_subbatches(len(my_ids), sub_e2e, args.workers)       # short head: first kernels start early
-    pairs_sub = [distinct[j % len(distinct)] for j in range(sub)]
-    pinned = nbatch.pin_pairs(pairs_sub, SR)
-    resident = [nbatch.upload(pinned, k) for k in sizes]       # `value`: inputs already in HBM
+    # the rank's pairs in pinned host memory (the contract's e2e starts here) and resident in HBM (`value`)
+    pinned = nbatch.pin_pairs(pairs_np, SR)
+    n_mine = len(my_ids)
+    sub = max(1, min(args.sub_batch, max(16, -(-n_mine // 4)))) if n_mine else 1     # at least ~4 sub-batches per rank
+    sizes = [min(sub, n_mine - s) for s in range(0, n_mine, sub)]
+    starts = [sum(sizes[:j]) for j in range(len(sizes))]
+    resident = [nbatch.upload(pinned, k, start_pair=s) for s, k in zip(starts, sizes)]
     torch.cuda.synchronize()
     resident_bytes = sum(st.h2d_bytes for st in resident)
+    sizes_e2e = nbatch.plan_subbatches(n_mine, sub, args.workers, first=max(8, min(sub, n_mine // 12)))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def merge(total, stats):
-        for k, v in stats.items():
-            total[k] = total.get(k, 0) + v
-
     def step_resident():
         stats = {}
         res = nbatch.analyse_resident(resident, stats=stats, workers=args.workers, **kw)
         return res, stats
 
-    def step_e2e():
-        # pinned host → HBM inside the timed region; results come back as host objects.  Sub-batches are dealt to
-        # `--workers` host threads / CUDA streams, so copies and host stages of one overlap kernels of another.
+    def step_e2e(source):
+        # the public batch API: pinned (or pageable) host arrays in, host results out; staging, H2D copies and the
+        # analysis of different sub-batches overlap inside the call
         stats = {}
-        res = nbatch.analyse_pinned(pinned, sizes_e2e, stats=stats, workers=args.workers, **kw)
-        return res, stats, stats["h2d_bytes"]
+        res = na.run_batch(source, SR, sub_batch=sub, workers=args.workers, stats=stats, **kw)
+        return res, stats
 
     # ---- device-resident timing (value)
     for _ in range(args.warmup):
@@ -245,7 +280,6 @@ def run_gpu(args):
     windows = stats["windows"]
 
     # ---- per-kernel shares and the front-end roofline: one extra step with the library's event profiler on
-    from nightcore_analyzer import _native
     # (single host worker here: with two streams the event brackets of one stream would include the other's kernels)
     _native.lib.ncfa_profile_enable(1)
     pstats = {}
@@ -255,49 +289,69 @@ def run_gpu(args):
     _native.lib.ncfa_profile_enable(0)
     roof = npar.frontend_roofline(prof, pstats)
 
-    # ---- end-to-end timing through the host-buffer API
-    for _ in range(min(args.warmup, 2)):
-        step_e2e()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(args.steps):
-        res_e, stats_e, h2d = step_e2e()
-    e1.record()
-    barrier()
-    ms_e2e = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)) / args.steps
-    d2h = npar.result_bytes(stats_e)
+    # ---- end-to-end timing through the public API, pinned host buffers
+    def time_e2e(source, warm, steps):
+        for _ in range(warm):
+            step_e2e(source)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            r, s = step_e2e(source)
+        e1.record()
+        barrier()
+        return max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)) / steps, r, s
+
+    ms_e2e, res_e, stats_e = time_e2e(pinned, min(args.warmup, 3), args.steps)
+    windows_e = stats_e["windows"]
+    h2d, d2h = stats_e["h2d_bytes"], npar.result_bytes(stats_e)
+    if args.no_pageable:
+        ms_page, windows_p = None, 0
+    else:
+        ms_page, _, stats_p = time_e2e(pairs_np, 1, max(1, min(args.steps, 2)))
+        windows_p = stats_p["windows"]
 
     # ---- max over ranks, totals over ranks
     if world > 1:
-        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms, ms_e2e, ms_page or 0.0], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
-        c = torch.tensor([windows, len(my_ids), n_ok, h2d, d2h, launches], dtype=torch.float64, device="cuda")
+        ms, ms_e2e, ms_page = float(t[0]), float(t[1]), (float(t[2]) if ms_page is not None else None)
+        c = torch.tensor([windows, n_mine, n_ok, h2d, d2h, launches, windows_e, windows_p], dtype=torch.float64, device="cuda")
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        windows, n_pairs_all, n_ok, h2d, d2h, launches = (int(x) for x in c.tolist())
-        gathered = npar.gather_result_records(res, my_ids, total_pairs)   # the NCCL gather of per-pair records
+        windows, n_pairs_all, n_ok, h2d, d2h, launches, windows_e, windows_p = (int(x) for x in c.tolist())
+        gathered = npar.gather_result_records(res_e, my_ids, total_pairs)   # the NCCL gather of per-pair records
     else:
-        n_pairs_all = len(my_ids)
+        n_pairs_all = n_mine
+        gathered = npar.records_of(res_e)
 
     if rank == 0:
+        # N-rank identity: every gathered row must equal the record of the same pair analysed ALONE on this rank
+        alone = npar.records_of(na.run_batch([distinct[i] for i in range(n_distinct)], SR, **kw))
+        want = alone[np.arange(total_pairs) % n_distinct]
+        gather_identical = bool(gathered.shape == want.shape and
+                                np.array_equal(np.nan_to_num(gathered, nan=-1.0), np.nan_to_num(want, nan=-1.0)))
         peak, peak_kind = load_peaks()
         traffic, traffic_src = load_traffic("stft_logmel_kernel[hop<=128]")
         value = windows / (ms / 1e3)
+        pps = n_pairs_all / (ms / 1e3)
+        pps_e = n_pairs_all / (ms_e2e / 1e3)
         line = {
             "metric": "analysis_windows_per_sec", "value": value, "unit": "windows/s",
-            "pairs_per_sec": n_pairs_all / (ms / 1e3), "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "pairs_per_sec": pps, "audio_sec_per_sec": audio_seconds(pps, args.pair_sec), "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": f"synthetic ({len(distinct)} distinct pairs tiled to {total_pairs}; oracle/synth.py)",
-            "config": {"workload": WORKLOAD, "pairs": total_pairs, "pair_sec": args.pair_sec, "sr": SR,
-                       "sub_batch_pairs": sub, "e2e_sub_batches": sizes_e2e, "host_workers": args.workers, "windows_per_step": windows, "pairs_ok": n_ok,
-                       "pitch": not args.no_pitch, "ibi": not args.no_ibi,
-                       "l2": "inputs larger than L2 (resident audio per rank %.0f MB > 126 MB)" % (resident_bytes / 1e6)
-                       if resident_bytes > (126 << 20) else "inputs smaller than L2 (reduced --pairs run)"},
-            "e2e": {"value": windows / (ms_e2e / 1e3), "unit": "windows/s", "ms_per_step": ms_e2e,
-                    "pairs_per_sec": n_pairs_all / (ms_e2e / 1e3), "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h)},
+            "data": f"synthetic ({n_distinct} distinct pairs tiled to {total_pairs}; oracle/synth.py)",
+            "config": workload_config(total_pairs, args.pair_sec),
+            "schedule": {"sub_batch_pairs": sub, "resident_sub_batches": sizes, "e2e_sub_batches": sizes_e2e,
+                         "host_workers": args.workers, "windows_per_step": windows, "pairs_ok": n_ok,
+                         "pitch": not args.no_pitch, "ibi": not args.no_ibi,
+                         "resident_audio_mb_per_rank": round(resident_bytes / 1e6, 1)},
+            "e2e": {"value": windows_e / (ms_e2e / 1e3), "unit": "windows/s", "ms_per_step": ms_e2e,
+                    "pairs_per_sec": pps_e, "audio_sec_per_sec": audio_seconds(pps_e, args.pair_sec),
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "api": "nightcore_analyzer.run_batch(PinnedBatch) — pinned host memory in, AnalysisResult objects out"},
+            "gather_identical": gather_identical,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": roof["gbs"], "peak": peak, "unit": "GB/s",
                          "frac": roof["gbs"] / peak, "traffic": traffic, "peak_kind": peak_kind,
@@ -311,14 +365,21 @@ def run_gpu(args):
             "kernels": roof["table"],
             "clocks": clk.summary(),
         }
-        if not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
+        if ms_page is not None:
+            pps_p = n_pairs_all / (ms_page / 1e3)
+            line["e2e_pageable"] = {"value": windows_p / (ms_page / 1e3), "unit": "windows/s", "ms_per_step": ms_page,
+                                    "pairs_per_sec": pps_p,
+                                    "api": "nightcore_analyzer.run_batch(list of numpy array pairs) — pageable memory in"}
+        if not args.no_cpu_baseline and world == 1:
             procs = max(1, min(cores, args.cpu_procs or cores))
-            w, p, wall, nwin = cpu_throughput(procs, args.cpu_dur, procs)
-            line["cpu_baseline"] = {"value": w, "unit": "windows/s", "cores": procs, "kind": "port",
-                                    "pairs_per_sec": p,
-                                    "sample": f"{procs} pairs of {args.cpu_dur:.0f}s source + 1.25x nightcore, one pair "
-                                              f"per process, {wall:.1f}s wall"}
+            arm = CpuArm(args.pair_sec, procs, args.cpu_sample or max(1, procs // 4), distinct)
+            try:
+                w, n, wall = arm.step()
+            finally:
+                arm.close()
+            line["cpu_baseline"] = {"value": w / wall, "unit": "windows/s", "cores": procs, "kind": "port",
+                                    "pairs_per_sec": n / wall, "audio_sec_per_sec": audio_seconds(n / wall, args.pair_sec),
+                                    "sample": arm.sample_text() + f"; one step, {wall:.1f} s wall"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -330,7 +391,7 @@ def run_single_pair(args):
     import torch
     from nightcore_analyzer import pipeline as npipe
     from oracle import pipeline_port
-    nc, src = make_pairs(1, args.pair_sec)[0]
+    nc, src = make_pairs([0], args.pair_sec, 1)[0]
     for _ in range(2):
         res = npipe.run_arrays(nc, src, SR, log=None)
     torch.cuda.synchronize()
@@ -356,6 +417,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
+    ap.add_argument("--config", type=int, default=5, choices=[2, 3, 4, 5], help="BASELINE config (5 = the contract line)")
     ap.add_argument("--pairs", type=int, default=1000, help="total track pairs per step (all ranks)")
     ap.add_argument("--pair-sec", type=float, default=PAIR_SEC)
     ap.add_argument("--sub-batch", type=int, default=125, help="pairs analysed per device pass (per rank)")
@@ -363,16 +425,19 @@ def main():
     ap.add_argument("--no-pitch", action="store_true")
     ap.add_argument("--no-ibi", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-dur", type=float, default=30.0, help="source seconds per CPU-baseline pair")
+    ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-memory e2e figure")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="pairs per CPU step (default: cores // 4)")
     ap.add_argument("--cpu-procs", type=int, default=0)
     ap.add_argument("--single-pair", action="store_true", help="config 1: latency of one pair through pipeline.run_arrays")
     args = ap.parse_args()
     if args.single_pair:
         return run_single_pair(args)
     if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_gpu(args)
+        return run_reference(args)
+    if args.config != 5:
+        import bench_families
+        return bench_families.run(args)
+    run_gpu(args)
 
 
 if __name__ == "__main__":

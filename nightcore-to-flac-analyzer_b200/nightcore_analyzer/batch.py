@@ -19,6 +19,8 @@ exception object in the result list and does not disturb the others.
 """
 from __future__ import annotations
 
+import queue
+import threading
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple, Union
 
@@ -68,27 +70,35 @@ def pin_pairs(pairs: Sequence[Tuple[np.ndarray, np.ndarray]], sr: int = SAMPLE_R
     total = int(padded.sum()) if len(tracks) else 0
     if pinned is None or pinned.numel() < max(total, 4):
         pinned = torch.empty(max(total, 4), dtype=torch.float32, pin_memory=True)
-    hn = pinned.numpy()
-    for t, o in zip(tracks, off):
-        hn[o : o + len(t)] = t
+    for t, o in zip(tracks, off):     # torch's host copy is multi-threaded (numpy's slice assignment is not)
+        pinned[o : o + len(t)].copy_(torch.from_numpy(np.ascontiguousarray(t)))
     return PinnedBatch(pinned=pinned, off=off, length=length, sr=sr)
 
 
-def upload(pb: PinnedBatch, n_pairs: Optional[int] = None, out: Optional[torch.Tensor] = None) -> StagedBatch:
-    """One asynchronous H2D copy of the first ``n_pairs`` pairs of a pinned batch (into ``out`` when given: a
-    preallocated device buffer avoids allocator traffic — and its implicit synchronisations — in a streaming loop)."""
+def upload(pb: PinnedBatch, n_pairs: Optional[int] = None, out: Optional[torch.Tensor] = None,
+           start_pair: int = 0) -> StagedBatch:
+    """One asynchronous H2D copy of pairs ``[start_pair, start_pair + n_pairs)`` of a pinned batch (into ``out`` when
+    given: a preallocated device buffer avoids allocator traffic — and its implicit synchronisations — in a streaming
+    loop).  Offsets of the returned batch are relative to its own buffer."""
     eng = _engine.get_engine()
-    k = pb.n_pairs if n_pairs is None else min(int(n_pairs), pb.n_pairs)
-    off, length = pb.off[: 2 * k], pb.length[: 2 * k]
-    total = int(off[-1] + (length[-1] + 3) // 4 * 4) if k else 0
+    s = int(start_pair)
+    if s < 0 or s > pb.n_pairs:
+        raise ValueError(f"start_pair {s} outside the pinned batch of {pb.n_pairs} pairs")
+    k = pb.n_pairs - s if n_pairs is None else int(n_pairs)
+    if k < 0 or s + k > pb.n_pairs:
+        raise ValueError(f"pairs [{s}, {s + k}) outside the pinned batch of {pb.n_pairs} pairs")
+    off, length = pb.off[2 * s : 2 * (s + k)], pb.length[2 * s : 2 * (s + k)]
+    base = int(off[0]) if k else 0
+    total = int(off[-1] + (length[-1] + 3) // 4 * 4) - base if k else 0
     n = max(total, 4)
+    src = pb.pinned[base : base + n] if base + n <= pb.pinned.numel() else pb.pinned[base:]
     if out is not None and out.numel() >= n:
-        audio = out[:n]
-        audio.copy_(pb.pinned[:n], non_blocking=True)
+        audio = out[: src.numel()]
+        audio.copy_(src, non_blocking=True)
     else:
-        audio = pb.pinned[:n].to(eng.device, non_blocking=True)
+        audio = src.to(eng.device, non_blocking=True)
     eng.h2d_bytes += 4 * total
-    return StagedBatch(audio=audio, off=off.copy(), length=length.copy(), sr=pb.sr, h2d_bytes=4 * total)
+    return StagedBatch(audio=audio, off=off - base, length=length.copy(), sr=pb.sr, h2d_bytes=4 * total)
 
 
 def stage_pairs(pairs: Sequence[Tuple[np.ndarray, np.ndarray]], sr: int = SAMPLE_RATE,
@@ -284,14 +294,9 @@ def analyse_staged(batch: StagedBatch, *, window_sec: float = WINDOW_SEC, hop_se
     return results
 
 
-def run_batch_arrays(pairs: Sequence[Tuple[np.ndarray, np.ndarray]], sr: int = SAMPLE_RATE, **kwargs):
-    """[(nc_audio, src_audio), ...] → [AnalysisResult | Exception, ...] (same kwargs as analyse_staged)."""
-    return analyse_staged(stage_pairs(pairs, sr), **kwargs)
-
-
 def plan_subbatches(n_pairs: int, sub: int, workers: int = 2, first: int = 8, growth: float = 1.5) -> List[int]:
     """Sub-batch sizes for ``n_pairs`` pairs, at most ``sub`` each.  A job can start only when its upload is complete,
-    and the upload of a worker's next job runs while its current one computes; the copy engine moves a pair about twice
+    and the upload of the next job runs while the current ones compute; the copy engine moves a pair about twice
     as fast as the kernels analyse one, so sizes grow geometrically (``first``, x ``growth`` < 2) until they reach
     ``sub``: every upload hides behind the compute of the jobs before it and only the first few pairs' copy is
     exposed.  The rest is split evenly (no short tail job)."""
@@ -310,47 +315,205 @@ def plan_subbatches(n_pairs: int, sub: int, workers: int = 2, first: int = 8, gr
     return sizes
 
 
-def run_subbatches(jobs: Sequence, fn, workers: int = 2, prepare=None) -> list:
+# ------------------------------------------------------------------------------------------------ the batch scheduler
+# One stager thread walks the jobs (consecutive, disjoint slices of the batch) in order: it lays a slice out in pinned
+# memory when the caller's arrays are pageable, queues its host→HBM copy on a copy stream into one of `workers + 1`
+# preallocated device slots and hands (StagedBatch, copy-done event) to whichever of the `workers` analysis threads is
+# free.  Each analysis thread has its own CUDA stream and Engine (workspaces, pinned parameter ring), so while one waits
+# for a small device→host read or assembles results the other keeps the GPU fed, and copies never sit in front of kernels.
+SUB_BATCH_PAIRS = 125        # pairs analysed per device pass (3.6 GB of audio at 180 s + 144 s per pair)
+INLINE_PAIRS = 8             # batches up to this size are analysed in the calling thread, in one pass
+
+
+class _Slot:
+    def __init__(self, device, n_floats: int, want_pinned: bool):
+        self.dev = torch.empty(max(n_floats, 4), dtype=torch.float32, device=device)
+        self.pinned = torch.empty(max(n_floats, 4), dtype=torch.float32, pin_memory=True) if want_pinned else None
+        self.free = torch.cuda.Event()       # recorded by the analysis stream that last read `dev`
+
+
+_SLOTS: dict = {}
+_SCHED_LOCK = threading.Lock()
+
+
+def _slots_for(device, n_slots: int, n_floats: int, want_pinned: bool) -> List[_Slot]:
+    """Device (and, for pageable input, pinned staging) slots, cached across calls and grown on demand."""
+    key = torch.device(device).index
+    cur = _SLOTS.get(key, [])
+    ok = (len(cur) >= n_slots and all(s.dev.numel() >= n_floats for s in cur[:n_slots]) and
+          (not want_pinned or all(s.pinned is not None and s.pinned.numel() >= n_floats for s in cur[:n_slots])))
+    if not ok:
+        keep_pinned = want_pinned or any(s.pinned is not None for s in cur)
+        size = max([n_floats] + [s.dev.numel() for s in cur])
+        _SLOTS[key] = cur = []          # drop the old buffers before allocating the new ones
+        cur += [_Slot(device, size, keep_pinned) for _ in range(n_slots)]
+        _SLOTS[key] = cur
+    return cur[:n_slots]
+
+
+def release_buffers() -> None:
+    """Free the cached device / pinned staging slots of the scheduler."""
+    with _SCHED_LOCK:
+        _SLOTS.clear()
+
+
+def _layout(lengths: np.ndarray) -> Tuple[np.ndarray, int]:
+    padded = (lengths + 3) // 4 * 4
+    off = np.zeros(len(lengths), dtype=np.int64)
+    if len(lengths) > 1:
+        off[1:] = np.cumsum(padded)[:-1]
+    return off, int(padded.sum()) if len(lengths) else 0
+
+
+def analyse_batch(source, sr: int = SAMPLE_RATE, *, sub_batch: int = SUB_BATCH_PAIRS, workers: int = 2,
+                  sizes: Optional[Sequence[int]] = None, stats: Optional[dict] = None, **kwargs):
+    """Analyse every pair of ``source`` — a ``PinnedBatch`` (pin_pairs) or a sequence of ``(nc_audio, src_audio)``
+    numpy arrays — and return one AnalysisResult (or exception object) per pair, in order.  The batch is cut into
+    consecutive sub-batches (``sizes``, default ``plan_subbatches``) that stream through HBM: staging (pageable →
+    pinned, multi-threaded), host→device copy and analysis of different sub-batches overlap."""
+    pinned_in = isinstance(source, PinnedBatch)
+    if pinned_in:
+        sr = source.sr
+        P = source.n_pairs
+        lengths = source.length
+    else:
+        tracks = [np.ascontiguousarray(t, dtype=np.float32) for p in source for t in p]
+        P = len(tracks) // 2
+        lengths = np.array([len(t) for t in tracks], dtype=np.int64)
+    if P == 0:
+        return []
+    if sizes is None:
+        sizes = [P] if P <= INLINE_PAIRS else plan_subbatches(P, sub_batch, workers)
+    sizes = [int(k) for k in sizes]
+    if any(k <= 0 for k in sizes) or sum(sizes) != P:
+        raise ValueError(f"sub-batch sizes {sizes} do not cover the {P} pairs of the batch exactly once")
+    starts = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(int)
+
+    if len(sizes) == 1:      # one pass in the calling thread
+        st = upload(source) if pinned_in else stage_pairs(list(source), sr)
+        s1: dict = {}
+        res = analyse_staged(st, stats=s1, **kwargs)
+        if stats is not None:
+            s1["h2d_bytes"] = st.h2d_bytes
+            for key, v in s1.items():
+                stats[key] = stats.get(key, 0) + v
+        return res
+
+    eng = _engine.get_engine()
+    device = eng.device
+    main = torch.cuda.current_stream(device)
+    nw = max(1, min(int(workers), len(sizes)))
+    need = max(_layout(lengths[2 * s : 2 * (s + k)])[1] for s, k in zip(starts, sizes))
+    with _SCHED_LOCK:       # one scheduled batch per process at a time (the slots are shared)
+        slots = _slots_for(device, nw + 1, need, want_pinned=not pinned_in)
+        free_q: "queue.Queue[_Slot]" = queue.Queue()
+        for sl in slots:
+            sl.free.record(main)
+            free_q.put(sl)
+        ready_q: "queue.Queue" = queue.Queue()
+        copy_stream = _worker_stream(device, 100)
+        copy_stream.wait_stream(main)
+        out: list = [None] * len(sizes)
+        errors: list = []
+
+        def stager():
+            try:
+                torch.cuda.set_device(device)
+                for j, (s, k) in enumerate(zip(starts, sizes)):
+                    sl = free_q.get()
+                    if errors:
+                        break
+                    ln = lengths[2 * s : 2 * (s + k)]
+                    if pinned_in:
+                        base = int(source.off[2 * s])
+                        off = source.off[2 * s : 2 * (s + k)] - base
+                        total = int(off[-1] + (ln[-1] + 3) // 4 * 4)
+                        src = source.pinned[base : base + total]
+                    else:
+                        off, total = _layout(ln)
+                        for t, o in zip(tracks[2 * s : 2 * (s + k)], off):   # torch's copy is multi-threaded
+                            sl.pinned[o : o + len(t)].copy_(torch.from_numpy(t))
+                        src = sl.pinned[:total]
+                    with torch.cuda.stream(copy_stream):
+                        copy_stream.wait_event(sl.free)
+                        sl.dev[:total].copy_(src, non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(copy_stream)
+                    ready_q.put((j, StagedBatch(audio=sl.dev[: max(total, 4)], off=off.copy(), length=ln.copy(), sr=sr,
+                                                h2d_bytes=4 * total), ev, sl))
+            except BaseException as e:  # noqa: BLE001
+                errors.append(e)
+            finally:
+                for _ in range(nw):
+                    ready_q.put(None)
+
+        def worker(w: int):
+            torch.cuda.set_device(device)
+            stream = _worker_stream(device, w)
+            stream.wait_stream(main)
+            with torch.cuda.stream(stream):
+                while True:
+                    item = ready_q.get()
+                    if item is None:
+                        break
+                    j, st, ev, sl = item
+                    try:
+                        stream.wait_event(ev)
+                        s1: dict = {}
+                        res = analyse_staged(st, stats=s1, **kwargs)
+                        s1["h2d_bytes"] = st.h2d_bytes
+                        out[j] = (res, s1)
+                    except BaseException as e:  # noqa: BLE001
+                        errors.append(e)
+                    finally:
+                        sl.free.record(stream)
+                        free_q.put(sl)
+                stream.synchronize()
+
+        futs = [_worker_thread(device, 100).submit(stager)] + [_worker_thread(device, w).submit(worker, w) for w in range(nw)]
+        for f in futs:
+            f.result()
+        for w in range(nw):
+            main.wait_stream(_worker_stream(device, w))
+    if errors:
+        raise errors[0]
+    results: list = []
+    for res, s1 in out:
+        results += res
+        if stats is not None:
+            for key, v in s1.items():
+                stats[key] = stats.get(key, 0) + v
+    return results
+
+
+def run_batch_arrays(pairs, sr: int = SAMPLE_RATE, **kwargs):
+    """[(nc_audio, src_audio), ...] or a PinnedBatch → [AnalysisResult | Exception, ...] (kwargs of analyse_batch)."""
+    return analyse_batch(pairs, sr, **kwargs)
+
+
+def run_subbatches(jobs: Sequence, fn, workers: int = 2) -> list:
     """Run ``fn(x)`` for every job on ``workers`` host threads, each with its own CUDA stream and engine, and return
-    the results in job order.  While one thread waits for a device→host read or assembles results, the other keeps the
-    GPU fed.  With ``prepare`` (job → StagedBatch, an H2D upload) each worker stages its NEXT job on a separate copy
-    stream before it analyses the current one, so copies never sit in front of kernels."""
-    import concurrent.futures as cf
+    the results in job order (sub-batches that already live in HBM)."""
     eng = _engine.get_engine()
     device = eng.device
     main = torch.cuda.current_stream(device)
     workers = max(1, min(workers, len(jobs)))
     streams = [_worker_stream(device, w) for w in range(workers)]
-    copies = [_worker_stream(device, 100 + w) for w in range(workers)]
-    for st in streams + copies:
+    for st in streams:
         st.wait_stream(main)
     out: list = [None] * len(jobs)
+    nxt = iter(range(len(jobs)))
+    lock = threading.Lock()
 
     def work(w: int):
         torch.cuda.set_device(device)
-        mine = list(range(w, len(jobs), workers))
-
-        def stage(i):
-            if prepare is None:
-                return jobs[i], None
-            copies[w].wait_stream(streams[w])      # the allocator may hand out a block last used by this worker's kernels
-            with torch.cuda.stream(copies[w]):
-                x = prepare(jobs[i], w, stage.count)
-                stage.count += 1
-                ev = torch.cuda.Event()
-                ev.record(copies[w])
-            return x, ev
-
-        stage.count = 0
-        nxt = stage(mine[0]) if mine else None
         with torch.cuda.stream(streams[w]):
-            for n, i in enumerate(mine):
-                x, ev = nxt
-                if ev is not None:
-                    streams[w].wait_event(ev)
-                    x.audio.record_stream(streams[w])
-                nxt = stage(mine[n + 1]) if n + 1 < len(mine) else None
-                out[i] = fn(x)
+            while True:
+                with lock:
+                    i = next(nxt, None)
+                if i is None:
+                    break
+                out[i] = fn(jobs[i])
             streams[w].synchronize()
 
     if workers == 1:
@@ -364,41 +527,8 @@ def run_subbatches(jobs: Sequence, fn, workers: int = 2, prepare=None) -> list:
     return out
 
 
-def analyse_pinned(pb: PinnedBatch, sizes: Sequence[int], stats: Optional[dict] = None, workers: int = 2, **kwargs):
-    """End-to-end form of the batch scheduler: the pairs of a pinned host batch are analysed in sub-batches of
-    ``sizes`` pairs each (every sub-batch reads the first ``k`` pairs of ``pb`` — bench.py tiles one composition).
-    Sub-batches are dealt to ``workers`` host threads / CUDA streams; every worker uploads its next sub-batch
-    (pinned → HBM, separate copy stream) while it analyses the current one."""
-    def one(st):
-        s1: dict = {}
-        res = analyse_staged(st, stats=s1, **kwargs)
-        s1["h2d_bytes"] = st.h2d_bytes
-        return res, s1
-
-    # two preallocated device buffers per worker: slot n is reused for the worker's job n+2, which is uploaded while
-    # job n+1 runs, i.e. after job n has delivered its results
-    eng = _engine.get_engine()
-    kmax = max(sizes) if sizes else 0
-    need = int(pb.off[2 * kmax - 1] + (pb.length[2 * kmax - 1] + 3) // 4 * 4) if kmax else 4
-    nw = max(1, min(workers, len(sizes)))
-    key = (eng.device.index, nw, need)
-    if _UPLOAD_BUFFERS.get("key") != key:
-        _UPLOAD_BUFFERS.clear()
-        _UPLOAD_BUFFERS["key"] = key
-        _UPLOAD_BUFFERS["buf"] = [[torch.empty(max(need, 4), dtype=torch.float32, device=eng.device) for _ in range(2)]
-                                  for _ in range(nw)]
-    bufs = _UPLOAD_BUFFERS["buf"]
-    results: list = []
-    for res, s1 in run_subbatches(list(sizes), one, workers, prepare=lambda k, w, n: upload(pb, k, out=bufs[w][n % 2])):
-        results += res
-        if stats is not None:
-            for key, v in s1.items():
-                stats[key] = stats.get(key, 0) + v
-    return results
-
-
 def analyse_resident(batches: Sequence[StagedBatch], stats: Optional[dict] = None, workers: int = 2, **kwargs):
-    """Same scheduler for sub-batches that already live in HBM."""
+    """Same analysis threads for sub-batches that already live in HBM."""
     def one(st):
         s1: dict = {}
         return analyse_staged(st, stats=s1, **kwargs), s1
@@ -413,9 +543,6 @@ def analyse_resident(batches: Sequence[StagedBatch], stats: Optional[dict] = Non
 
 
 _WORKER_STREAMS: dict = {}
-_UPLOAD_BUFFERS: dict = {}
-
-
 _WORKER_THREADS: dict = {}
 
 

@@ -187,7 +187,7 @@ def run(
 
 
 def run_batch(
-    pairs: Sequence[Tuple[np.ndarray, np.ndarray]],
+    pairs,
     sr: int = SAMPLE_RATE,
     *,
     window_sec: float = WINDOW_SEC,
@@ -195,9 +195,17 @@ def run_batch(
     energy_gate_db: float = ENERGY_GATE_DB,
     silence_strip_db: Optional[float] = SILENCE_STRIP_DB,
     compute_pitch: bool = True,
+    compute_ibi: bool = True,
+    sub_batch: Optional[int] = None,
+    workers: int = 2,
+    stats: Optional[dict] = None,
 ) -> List[Union[AnalysisResult, Exception]]:
     """[(nc_audio, src_audio), ...] → one AnalysisResult (or the exception ``run`` would raise) per pair,
-    computed stage by stage over the whole batch (batch.analyse_staged)."""
+    computed stage by stage over sub-batches that stream through HBM (batch.analyse_batch): staging, host→device
+    copies and analysis of different sub-batches overlap.  ``pairs`` is a sequence of numpy array pairs or a
+    ``batch.PinnedBatch`` (``batch.pin_pairs``: the same pairs already laid out in pinned host memory, which skips the
+    staging copy).  ``stats`` (optional dict) receives counters: windows, tracks, h2d_bytes, d2h_bytes, hop64_frames."""
     from . import batch
-    return batch.run_batch_arrays(pairs, sr, window_sec=window_sec, hop_sec=hop_sec, energy_gate_db=energy_gate_db,
-                                  silence_strip_db=silence_strip_db, compute_pitch=compute_pitch)
+    return batch.analyse_batch(pairs, sr, sub_batch=sub_batch or batch.SUB_BATCH_PAIRS, workers=workers, stats=stats,
+                               window_sec=window_sec, hop_sec=hop_sec, energy_gate_db=energy_gate_db,
+                               silence_strip_db=silence_strip_db, compute_pitch=compute_pitch, compute_ibi=compute_ibi)

@@ -232,17 +232,24 @@ def tempogram_mean(onset_envelope: np.ndarray, win_length: int, block: int = 204
     return acc / n
 
 
-def tempo_lag(onset_envelope: np.ndarray, sr: float = 22050, hop_length: int = 512, start_bpm: float = 120.0,
-              std_bpm: float = 1.0, ac_size: float = 8.0, max_tempo: float = 320.0) -> int:
-    """Best autocorrelation lag of librosa.feature.tempo (Appendix A.3) — tempo.py:63."""
-    win_length = int(np.floor(ac_size * sr / hop_length))
-    tg = tempogram_mean(onset_envelope, win_length)
+def tempo_lag_from_mean(tg: np.ndarray, sr: float = 22050, hop_length: int = 512, start_bpm: float = 120.0,
+                        std_bpm: float = 1.0, max_tempo: float = 320.0) -> int:
+    """The prior-weighted argmax of librosa.feature.tempo over a time-averaged tempogram (Appendix A.3)."""
+    win_length = len(tg)
     bpms = tempo_frequencies(win_length, hop_length, sr)
     with np.errstate(divide="ignore"):
         logprior = -0.5 * ((np.log2(bpms) - np.log2(start_bpm)) / std_bpm) ** 2
     max_idx = int(np.argmax(bpms < max_tempo))
     logprior[:max_idx] = -np.inf
     return int(np.argmax(np.log1p(1e6 * tg) + logprior))
+
+
+def tempo_lag(onset_envelope: np.ndarray, sr: float = 22050, hop_length: int = 512, start_bpm: float = 120.0,
+              std_bpm: float = 1.0, ac_size: float = 8.0, max_tempo: float = 320.0) -> int:
+    """Best autocorrelation lag of librosa.feature.tempo (Appendix A.3) — tempo.py:63."""
+    win_length = int(np.floor(ac_size * sr / hop_length))
+    tg = tempogram_mean(onset_envelope, win_length)
+    return tempo_lag_from_mean(tg, sr, hop_length, start_bpm, std_bpm, max_tempo)
 
 
 def tempo(onset_envelope: np.ndarray, sr: float = 22050, hop_length: int = 512, start_bpm: float = 120.0) -> np.ndarray:
@@ -464,7 +471,10 @@ def estimate_tuning(y: np.ndarray, sr: float = 22050, bins_per_octave: int = 12,
         threshold = np.median(mag[pitch_mask])
     else:
         threshold = 0.0
-    return pitch_tuning(pitch[(mag >= threshold) & pitch_mask], bins_per_octave=bins_per_octave)
+    t = pitch_tuning(pitch[(mag >= threshold) & pitch_mask], bins_per_octave=bins_per_octave)
+    if return_index:  # histogram bin 0..99 (left edges -0.50 ... +0.49)
+        return t, int(round((t + 0.5) * 100))
+    return t
 
 
 def cqt_octave_basis(sr: float, fmin: float, bins_per_octave: int = 36, n_bins: int = 252, sparsity: float = 0.01):

@@ -4,7 +4,7 @@ CPU port of the reference's array-level pipeline (TEST / BASELINE INFRASTRUCTURE
 Same control flow and parameters as /root/reference/nightcore_analyzer/{io,tempo,pitch,consensus,
 pipeline}.py, executed on oracle/librosa_restated.py.  The reference itself cannot travel to the
 GPU box (and needs librosa), so this port is what ``bench.py --impl reference`` / ``cpu_baseline``
-time and what the full-pipeline parity tests compare against.  tests/test_reference_flow.py checks,
+time and what the full-pipeline parity tests compare against.  tests/test_reference_golden.py checks,
 in the build container, that the port agrees with the reference's own modules run unmodified over
 the librosa shim (oracle/reference_shim.py).
 
@@ -84,11 +84,8 @@ def estimate_tempo(y: np.ndarray, sr: int, start_bpm: float = 120.0, faithful_co
     return tempo_default if tempo_default > 0 else (tempo_tempogram if tempo_tempogram > 0 else None)
 
 
-def estimate_ibis_global(y: np.ndarray, sr: int, hop_length: int = IBI_HOP_LENGTH, min_ibis: int = 4,
-                         start_bpm: float = 120.0) -> Optional[np.ndarray]:
-    """tempo.py:120-173."""
-    onset_env = lr.onset_strength(y, sr, hop_length)
-    _, beat_frames = lr.beat_track(onset_env, sr, hop_length, start_bpm)
+def ibis_from_beats(beat_frames, sr: int, hop_length: int = IBI_HOP_LENGTH, min_ibis: int = 4) -> Optional[np.ndarray]:
+    """tempo.py:165-173."""
     beat_frames = np.atleast_1d(beat_frames)
     if len(beat_frames) < min_ibis + 1:
         return None
@@ -98,6 +95,14 @@ def estimate_ibis_global(y: np.ndarray, sr: int, hop_length: int = IBI_HOP_LENGT
     if len(ibis) < min_ibis:
         return None
     return ibis
+
+
+def estimate_ibis_global(y: np.ndarray, sr: int, hop_length: int = IBI_HOP_LENGTH, min_ibis: int = 4,
+                         start_bpm: float = 120.0) -> Optional[np.ndarray]:
+    """tempo.py:120-173."""
+    onset_env = lr.onset_strength(y, sr, hop_length)
+    _, beat_frames = lr.beat_track(onset_env, sr, hop_length, start_bpm)
+    return ibis_from_beats(beat_frames, sr, hop_length, min_ibis)
 
 
 # ---------------------------------------------------------------------------------- pitch.py

@@ -75,3 +75,77 @@ def make_pair(seed: int, dur_s: float = 180.0, sr: int = 22050, up: int = 4, dow
     src = synth(seed, dur_s, sr)
     nc = scipy.signal.resample_poly(src, up, down).astype(np.float32)
     return src, nc
+
+
+# ---------------------------------------------------------------------------------------------- stress corpus
+def _place(y: np.ndarray, times_s: np.ndarray, burst: np.ndarray, sr: int, gains=None) -> None:
+    """Add `burst` at each onset time (vectorised over onsets)."""
+    n = len(y)
+    starts = np.round(np.asarray(times_s) * sr).astype(np.int64)
+    starts = starts[(starts >= 0) & (starts < n)]
+    g = np.ones(len(starts)) if gains is None else np.asarray(gains)[: len(starts)]
+    for k in range(len(burst)):
+        idx = starts + k
+        ok = idx < n
+        np.add.at(y, idx[ok], burst[k] * g[ok])
+
+
+def stress(seed: int, dur_s: float, sr: int = 22050) -> np.ndarray:
+    """Weakly periodic / noisy / tempo-drifting material for the parity stress corpus (tests/golden/
+    make_fullsize_golden.py, tests/test_gpu_stress.py).  Eight families, picked by ``seed % 8``; everything is drawn
+    from ``default_rng(seed)`` so the GPU box regenerates the same samples.  float32 mono, peak 0.8."""
+    rng = np.random.default_rng(seed)
+    kind = seed % 8
+    n = int(round(dur_s * sr))
+    t = np.arange(n) / sr
+    y = np.zeros(n, dtype=np.float64)
+    click = rng.standard_normal(int(0.006 * sr)) * np.exp(-np.arange(int(0.006 * sr)) / (0.0015 * sr))
+    thump = np.sin(2 * np.pi * 70.0 * np.arange(int(0.12 * sr)) / sr) * np.exp(-np.arange(int(0.12 * sr)) / (0.03 * sr))
+    bpm = float(rng.uniform(70.0, 180.0))
+    period = 60.0 / bpm
+    if kind == 0:      # noise with a slow, shallow amplitude modulation: almost no periodicity
+        y = rng.standard_normal(n) * (1.0 + 0.15 * np.sin(2 * np.pi * t / period + rng.uniform(0, 6.28)))
+    elif kind == 1:    # red-ish noise with faint clicks 20 dB below it
+        w = rng.standard_normal(n)
+        y = np.convolve(w, np.ones(8) / 8.0, mode="same") * 2.0
+        _place(y, np.arange(0.0, dur_s, period), click * 0.1, sr)
+    elif kind == 2:    # tempo drift: the beat period changes linearly by up to ±15 % over the signal
+        drift = float(rng.uniform(-0.15, 0.15))
+        times, cur = [], float(rng.uniform(0, period))
+        while cur < dur_s:
+            times.append(cur)
+            cur += period * (1.0 + drift * cur / dur_s)
+        _place(y, np.array(times), thump, sr)
+        _place(y, np.array(times), click * 0.5, sr)
+        y += rng.standard_normal(n) * 0.02
+    elif kind == 3:    # two competing click trains of nearly equal strength (3:2, 4:3 or a 5 % detune)
+        ratio = [1.5, 4.0 / 3.0, 1.05][int(rng.integers(0, 3))]
+        _place(y, np.arange(rng.uniform(0, period), dur_s, period), thump, sr)
+        _place(y, np.arange(rng.uniform(0, period), dur_s, period / ratio), thump * float(rng.uniform(0.8, 1.1)), sr)
+        y += rng.standard_normal(n) * 0.01
+    elif kind == 4:    # jittered beats (sigma 30 ms) with random accents
+        times = np.arange(0.0, dur_s, period) + rng.normal(0.0, 0.03, int(np.ceil(dur_s / period)))
+        _place(y, np.sort(times), thump, sr, gains=rng.uniform(0.3, 1.0, len(times)))
+        y += rng.standard_normal(n) * 0.03
+    elif kind == 5:    # sustained chord with tremolo, no percussive onsets
+        f0 = float(rng.uniform(110.0, 440.0))
+        for mult in (1.0, 1.26, 1.498, 2.0):
+            for h in range(1, 5):
+                y += np.sin(2 * np.pi * f0 * mult * h * t + rng.uniform(0, 6.28)) / h
+        y *= 1.0 + 0.3 * np.sin(2 * np.pi * float(rng.uniform(3.0, 8.0)) * t)
+        y += rng.standard_normal(n) * 0.005
+    elif kind == 6:    # bursts of beats separated by stretches of exact digital silence
+        times = np.arange(0.0, dur_s, period)
+        gate = (np.floor(times / (4 * period)) % 2) == 0
+        _place(y, times[gate], thump, sr)
+        _place(y, times[gate] + period / 2, click * 0.4, sr)
+    else:              # syncopated pattern + loud hiss (-20 dB)
+        pattern = np.array([0.0, 0.75, 1.5, 2.0, 2.75, 3.5]) * period
+        bars = np.arange(0.0, dur_s, 4 * period)
+        times = (bars[:, None] + pattern[None, :]).ravel()
+        _place(y, times, thump, sr, gains=rng.uniform(0.5, 1.0, len(times)))
+        y += rng.standard_normal(n) * 0.1
+    peak = float(np.max(np.abs(y)))
+    if peak > 0:
+        y *= 0.8 / peak
+    return y.astype(np.float32)
