@@ -385,6 +385,116 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+
+# --------------------------------------------------------------------------------------- per-family lines (configs 2-4)
+def run_family(args):
+    """BASELINE configs 2 / 3 / 4 as their own lines (not the contract line): one kernel family each, inputs resident
+    in HBM, CUDA events around K steps, per-kernel event times from the library profiler, roofline of the family's
+    dominant kernel on SURVEY §8(d)'s algorithmic figures."""
+    import scipy.signal
+    import torch
+    from nightcore_analyzer import _engine, _native, pitch as npitch, xcorr as nxcorr
+    from oracle import synth
+    torch.cuda.set_device(0)
+    eng = _engine.get_engine()
+    peak, peak_kind = load_peaks()
+    cfg = args.config
+    if cfg == 4:
+        sr, n_pairs = 44100, args.family_pairs or 16
+        base = []
+        for k in range(2):
+            a = np.tile(synth.synth(4000 + k, 60.0, sr, bpm=124.0 + k), 10)            # 10 minutes = 26 460 000 samples
+            b = scipy.signal.resample_poly(a, 1000, 1003).astype(np.float32)
+            b = (b + np.random.default_rng(k).standard_normal(len(b)).astype(np.float32) * 0.01).astype(np.float32)
+            base.append((a, b))
+        pairs = [base[i % 2] for i in range(n_pairs)]
+        audio, off, ln = eng.pack([t for p in pairs for t in p])
+        tabs = [nxcorr._search_tables(int(ln[2 * i]), int(ln[2 * i + 1]), sr, 20, 3.0, 0.05, 0.10) for i in range(n_pairs)]
+        win, stride = tabs[0][3], tabs[0][4]
+        a_pos = np.concatenate([off[2 * i] + t[0] + t[5] for i, t in enumerate(tabs)])
+        b_lo = np.concatenate([off[2 * i + 1] + t[0] + t[6] for i, t in enumerate(tabs)])
+        n_cand = np.concatenate([t[7] for t in tabs])
+        alg_bytes = float(sum(4 * (win + (int(c) - 1) * stride + win) for c in n_cand if c > 0))
+
+        def step():
+            return eng.xcorr_search_dev(audio, audio, a_pos, b_lo, n_cand, win, stride, nxcorr.XCORR_RMS_GATE)
+
+        def check(out):
+            bj = out[0].cpu().numpy()
+            return {"windows_matched": int((bj >= 0).sum()), "windows": int(len(bj))}
+        units, unit, metric, kernel = n_pairs, "pairs/s", "xcorr_pairs_per_sec", "xcorr_blocks_kernel"
+        workload = (f"config 4: waveform cross-correlation speed search, {n_pairs} pairs of 10 min at 44.1 kHz "
+                    f"(2 distinct, tiled), 20 windows x ~64 candidates of {win} samples each")
+        bound_note = "memory bound (0.5 flop/B): algorithmic bytes = per window, the A window + its B search span, once"
+    elif cfg == 2:
+        sr = SR
+        y = np.tile(synth.synth(2000, 60.0, sr), 60)                                  # 60 minutes = 79 380 000 samples
+        audio, off, ln = eng.pack([y])
+        frames = 1 + len(y) // 64
+        alg_bytes = float(frames * 260)
+
+        def step():
+            return eng.tempo_segments_dev(audio, off, ln, np.array([120.0]), 64, sr)
+
+        def check(out):
+            return {"lag": int(out[3].cpu().numpy()[0]), "beats": int(out[5].cpu().numpy()[0])}
+        units, unit, metric, kernel = frames, "frames/s", "hop64_frames_per_sec", "stft_logmel_kernel[hop<=128]"
+        workload = "config 2: hop-64 onset envelope + tempogram lag + beat tracking of one 60-minute track (1 240 313 frames)"
+        bound_note = "compute bound (AI 249 flop/B): FP32 fraction of the STFT kernel is the binding one"
+    else:
+        sr, n_pairs = SR, args.family_pairs or 125
+        distinct = make_pairs(range(min(N_DISTINCT, n_pairs)), args.pair_sec)
+        tracks = [t for i in range(n_pairs) for t in distinct[i % len(distinct)]]
+        audio, off, ln = eng.pack(tracks)
+        jobs = [(i, off[2 * i + 1], ln[2 * i + 1], off[2 * i], ln[2 * i]) for i in range(n_pairs)]
+        n_chunks = sum(2 * len(npitch._chunk_bounds(int(ln[2 * i + 1]), int(ln[2 * i]), sr)) for i in range(n_pairs))
+        alg_bytes = float(n_chunks * 1764048)
+
+        def step():
+            return npitch.chroma_shifts_staged(audio, jobs, sr)
+
+        def check(out):
+            return {"median_shift_st": float(np.median(np.concatenate(out)))}
+        units, unit, metric, kernel = n_chunks, "chunks/s", "chroma_chunks_per_sec", "cqt_tc_kernel"
+        workload = (f"config 3: CQT-chroma pitch stage (tuning, 6 decimations, 7-octave tcgen05 contraction, fold, cyclic "
+                    f"xcorr) of {n_pairs} pairs = {n_chunks} twenty-second chunks")
+        bound_note = "tensor-pipe kernel: see profiles/ for the ncu tensor-pipe utilisation"
+    for _ in range(max(3, args.warmup)):
+        out = step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = eng.launches
+    with ClockSampler(0) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            out = step()
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = (eng.launches - l0) // max(1, args.steps)
+    _native.lib.ncfa_profile_enable(1)
+    step()
+    torch.cuda.synchronize()
+    prof = _native.profile_report()
+    _native.lib.ncfa_profile_enable(0)
+    total = sum(v[1] for v in prof.values()) or 1e-9
+    table = {k: {"launches": v[0], "ms": round(v[1], 4), "share": round(v[1] / total, 4)}
+             for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+    kn, kms = prof.get(kernel, (1, ms))
+    fam_bytes = alg_bytes if cfg != 3 else alg_bytes
+    line = {"metric": metric, "value": units / (ms / 1e3), "unit": unit, "n_gpus": 1, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "dtype": "f32/f64",
+            "data": "synthetic (oracle/synth.py), resident in HBM", "config": {"workload": workload},
+            "gpu_launches": int(launches), "result": check(out),
+            "roofline": {"bound": "tensor" if cfg == 3 else "hbm", "kernel": kernel, "launches": kn,
+                         "ms_per_launch": kms / max(kn, 1), "algorithmic_bytes_per_step": fam_bytes,
+                         "achieved": fam_bytes / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": fam_bytes / (kms * 1e-3) / 1e9 / peak, "peak_kind": peak_kind, "traffic": None,
+                         "whole_step_gbs": fam_bytes / (ms * 1e-3) / 1e9, "note": bound_note},
+            "kernels": table, "clocks": clk.summary()}
+    print(json.dumps(line), flush=True)
+
+
 def run_single_pair(args):
     """BASELINE config 1 (the reference's own CPU-runnable case): latency of ONE 3-minute pair through the drop-in
     `pipeline.run_arrays` (host arrays in, AnalysisResult out) beside the CPU port on one core.  Not the contract line."""
@@ -428,6 +538,7 @@ def main():
     ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-memory e2e figure")
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs per CPU step (default: cores // 4)")
     ap.add_argument("--cpu-procs", type=int, default=0)
+    ap.add_argument("--family-pairs", type=int, default=0, help="pairs of the --config 3 / 4 family lines")
     ap.add_argument("--single-pair", action="store_true", help="config 1: latency of one pair through pipeline.run_arrays")
     args = ap.parse_args()
     if args.single_pair:
@@ -435,8 +546,7 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
     if args.config != 5:
-        import bench_families
-        return bench_families.run(args)
+        return run_family(args)
     run_gpu(args)
 
 

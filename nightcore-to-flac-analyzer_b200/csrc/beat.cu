@@ -275,12 +275,56 @@ __global__ void beat_track_kernel(const float *__restrict__ onset, const int64_t
             if (active) {
                 int lo = i - far;
                 if (lo < 0) lo = 0;
-#pragma unroll 4
-                for (int loc = i - near - sub; loc >= lo; loc -= L) {
-                    const double sc = cring[loc & rmask] - pen[i - loc - near];
-                    if (sc > best) {
-                        best = sc;
-                        bl = loc;
+                // element k of this lane: loc = first − L·k (nearest first), score = cring[loc] − pen[sub + L·k].
+                // The scan keeps only the running maximum and WHERE a group of four produced it (three max + one
+                // compare per four elements instead of a compare-and-select per element); the winning group is
+                // re-read at the end to find its first (nearest) element equal to the maximum — the scores are
+                // recomputed from the same operands, so the comparison is exact.
+                const int first_loc = i - near - sub;
+                const int n_el = first_loc >= lo ? (first_loc - lo) / L + 1 : 0;
+                int kbest = -1, wbest = 1;
+                if (n_el > 0) {
+                    const int idx0 = first_loc & rmask;
+                    int n1 = idx0 / L + 1;  // elements before the ring index wraps
+                    if (n1 > n_el) n1 = n_el;
+                    const double *pp = pen + sub;
+                    const double *cp = cring + idx0;
+                    int k = 0;
+#pragma unroll 1
+                    for (int part = 0; part < 2; ++part) {
+                        const int kend = part == 0 ? n1 : n_el;
+                        for (; k + 4 <= kend; k += 4) {
+                            const double s0 = cp[0] - pp[0];
+                            const double s1 = cp[-L] - pp[L];
+                            const double s2 = cp[-2 * L] - pp[2 * L];
+                            const double s3 = cp[-3 * L] - pp[3 * L];
+                            const double m = fmax(fmax(s0, s1), fmax(s2, s3));
+                            if (m > best) {
+                                best = m;
+                                kbest = k;
+                                wbest = 4;
+                            }
+                            cp -= 4 * L;
+                            pp += 4 * L;
+                        }
+                        for (; k < kend; ++k) {
+                            const double sc = cp[0] - pp[0];
+                            if (sc > best) {
+                                best = sc;
+                                kbest = k;
+                                wbest = 1;
+                            }
+                            cp -= L;
+                            pp += L;
+                        }
+                        cp += ring;  // the remaining elements sit one ring length higher
+                    }
+                    for (int kk = kbest; kk < kbest + wbest; ++kk) {
+                        const int loc = first_loc - L * kk;
+                        if (cring[loc & rmask] - pen[sub + L * kk] == best) {
+                            bl = loc;
+                            break;
+                        }
                     }
                 }
             }

@@ -557,6 +557,16 @@ constexpr int kCqtKT = 32;                                   // n (time-sample) 
 constexpr int kCqtThreads = 160;                             // 18 row groups × 8 frame groups = 144 active
 constexpr int kCqtSpanMax = (kCqtTF - 1) * 512 + kCqtNfft;   // widest sample span (octave 0)
 
+// |re + i·im| as np.abs(complex64) gives it (hypot): re² + im² underflows in float32 below ~1e-19, and a frame whose only
+// content is that small (the tail of a decayed note reaching the lowest octave of an otherwise digitally silent stretch)
+// is scaled up to 1 by the per-frame inf-norm — so tiny responses are squared after an exact rescale by 2^96.
+__device__ __forceinline__ float cabs_f32(float re, float im) {
+    const float a = fabsf(re), b = fabsf(im);
+    if (fmaxf(a, b) >= 0x1p-60f) return sqrtf(a * a + b * b);
+    const float as = a * 0x1p96f, bs = b * 0x1p96f;
+    return sqrtf(as * as + bs * bs) * 0x1p-96f;
+}
+
 struct CqtSmem {
     float sig[kCqtSpanMax + kCqtTF + kCqtNfft / 8 + 8];  // skewed: sample s lives at s + (s >> log2 hop)
     float kt[kCqtKT][kCqtRows];                          // K tile, n-major
@@ -645,7 +655,7 @@ __device__ __forceinline__ void cqt_octave(CqtSmem &sm, const float *__restrict_
         for (int q = 0; q < 3; ++q) {
             const int b = (3 * ch - 1 + q + kCqtBins) % kCqtBins;
             const float re = sm.c[b][t], im = sm.c[kCqtBins + b][t];
-            s += sqrtf(re * re + im * im);
+            s += cabs_f32(re, im);
         }
         sm.chroma[ch][t] += s;
     }
@@ -777,7 +787,7 @@ __device__ __forceinline__ void tc_epilogue_quarter(uint32_t acc_addr, float (&p
         const int b = 9 * Q + i;
         const int ch = ((b + 1) % kCqtBins) / 3;
         const int j = (ch - 3 * Q + kChroma) % kChroma;  // 0..3
-        part[j] += sqrtf(re[i] * re[i] + im[i] * im[i]);
+        part[j] += cabs_f32(re[i], im[i]);
     }
 }
 

@@ -85,6 +85,100 @@ __global__ void __launch_bounds__(kThreads, 1) stft_logmel_kernel(const float *_
     if (cur_seg >= 0 && lane == 0) atomicMax(seg_max + cur_seg, float_to_ordered(cur_max));
 }
 
+// ---- two frames per warp (the default form) ---------------------------------------------------------------------------
+// Same decomposition, but a warp owns the PAIR of frames (2p, 2p+1) of a segment and runs both through one instruction
+// stream (stft_core.cuh: warp_power_spectrum_global2): the Hann window, the W_1024 twiddles, W_2048^k and the mel
+// weights are read from shared memory once per pair, at hop 64 the two frames share 31 of their 32 register loads, and
+// the wider register budget (10 warps per SM instead of 20) removes the spills of the one-frame form.  Per frame:
+// ~340 shared-memory/L1 wavefronts instead of 510.  The per-frame arithmetic is unchanged, so the log-mel values — and
+// everything downstream — are bit-identical to the one-frame form (NCFA_STFT_IMPL=warp1, kept as a cross-check).
+constexpr int kWarps2Max = 12;  // 168 registers per thread × 384 threads fill the register file
+constexpr size_t kScrBytes2 = 2 * 32 * kScrStride * sizeof(float2);  // two transpose tiles per warp
+
+// dynamic shared memory: [hann 8 KB][tw 8 KB][lane_bin0 512 B][mel weights rows·128 B][scr: warps × 16.5 KB]
+__host__ __device__ inline size_t onset2_fixed_bytes(int mel_rows) { return 8192 + 8192 + 512 + (size_t)mel_rows * 128; }
+
+template <int SHIFT>
+__global__ void __launch_bounds__(kWarps2Max * 32, 1) stft_logmel2_kernel(const float *__restrict__ audio,
+                                                                    const int64_t *__restrict__ seg_off,
+                                                                    const int32_t *__restrict__ seg_len, int n_seg,
+                                                                    int hop, int frame_stride, Tables tb,
+                                                                    float *__restrict__ S, unsigned *__restrict__ seg_max) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    struct {
+        float *hann;
+        float2 *tw;
+        int *lane_bin0;
+        float *melwt;
+    } sm;
+    sm.hann = reinterpret_cast<float *>(smem_raw);
+    sm.tw = reinterpret_cast<float2 *>(smem_raw + 8192);
+    sm.lane_bin0 = reinterpret_cast<int *>(smem_raw + 16384);
+    sm.melwt = reinterpret_cast<float *>(smem_raw + 16896);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int kThreads2 = blockDim.x, kWarps2 = blockDim.x >> 5;
+    for (int i = tid; i < 2048; i += kThreads2) sm.hann[i] = tb.hann[i];
+    for (int i = tid; i < 1024; i += kThreads2) sm.tw[i] = tb.tw1024[i];
+    for (int i = tid; i < tb.mel_wt_rows * 32; i += kThreads2) sm.melwt[i] = tb.mel_wt[i];
+    for (int i = tid; i < 4 * 32; i += kThreads2) sm.lane_bin0[i] = tb.mel_lane_bin0[i];
+    __syncthreads();
+
+    const cf twl = cf{tb.tw2048[lane].x, tb.tw2048[lane].y};
+    float2 *scra = reinterpret_cast<float2 *>(smem_raw + onset2_fixed_bytes(tb.mel_wt_rows) + (size_t)warp * kScrBytes2);
+    float2 *scrb = scra + 32 * kScrStride;
+    const float *pa = reinterpret_cast<const float *>(scra), *pb = reinterpret_cast<const float *>(scrb);
+    int b0[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) b0[q] = sm.lane_bin0[q * 32 + lane];
+    const int pair_stride = (frame_stride + 1) >> 1;
+    const int64_t total = (int64_t)n_seg * pair_stride;
+    int cur_seg = -1;
+    float cur_max = -INFINITY;
+    // items (seg, frame pair) are dealt in groups of kWarps2 consecutive pairs per CTA (2·kWarps2 consecutive frames:
+    // L1 serves the overlap between them)
+    for (int64_t item = (int64_t)blockIdx.x * kWarps2 + warp; item < total; item += (int64_t)gridDim.x * kWarps2) {
+        const int seg = (int)(item / pair_stride);
+        const int fa = 2 * (int)(item - (int64_t)seg * pair_stride);
+        const int len = seg_len[seg];
+        const int n_frames = 1 + len / hop;
+        if (fa >= n_frames) continue;
+        const bool b_valid = fa + 1 < n_frames;
+        if (seg != cur_seg) {
+            if (cur_seg >= 0 && lane == 0) atomicMax(seg_max + cur_seg, float_to_ordered(cur_max));
+            cur_seg = seg;
+            cur_max = -INFINITY;
+        }
+        warp_power_spectrum_global2<SHIFT>(audio + seg_off[seg], (int64_t)fa * hop - 1024, hop, len, b_valid, sm.hann,
+                                           sm.tw, scra, scrb, twl, lane);
+        float *Sa = S + ((size_t)seg * frame_stride + fa) * NCFA_N_MELS;
+        float vmax = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float *wt = sm.melwt + (size_t)tb.mel_qoff[q] * 32 + lane;
+            const float *ka = pa + b0[q], *kb = pb + b0[q];
+            const int nw = tb.mel_qw[q];
+            float acca = 0.0f, accb = 0.0f;
+            for (int i = 0; i < nw; ++i) {  // zero weights beyond the band's support
+                const float w = wt[i * 32];
+                acca = fmaf(w, ka[i], acca);
+                accb = fmaf(w, kb[i], accb);
+            }
+            const float dba = 10.0f * log10f(fmaxf(1e-10f, acca));
+            const float dbb = 10.0f * log10f(fmaxf(1e-10f, accb));
+            const int band = mel_band_of(q, lane);
+            Sa[band] = dba;
+            vmax = fmaxf(vmax, dba);
+            if (b_valid) {
+                Sa[NCFA_N_MELS + band] = dbb;
+                vmax = fmaxf(vmax, dbb);
+            }
+        }
+        cur_max = fmaxf(cur_max, warp_max(vmax));
+        __syncwarp();
+    }
+    if (cur_seg >= 0 && lane == 0) atomicMax(seg_max + cur_seg, float_to_ordered(cur_max));
+}
+
 // onset[j] = 0 for j < pad;  else mean_m relu(clamp(S[j-pad+1][m]) - clamp(S[j-pad][m]))
 // A warp walks kFluxRun consecutive frames and keeps the previous log-mel row in registers, so every row is read from
 // L2 once (the kernel is L2-bandwidth bound: 512 B per frame).  Per frame: 4 bands per lane, then the xor tree.
@@ -264,6 +358,14 @@ static bool use_warp_form() {
     }();
     return v;
 }
+// NCFA_STFT_IMPL=warp1: the one-frame-per-warp form (cross-check of the two-frame default)
+static bool use_one_frame_form() {
+    static const bool v = [] {
+        const char *e = getenv("NCFA_STFT_IMPL");
+        return e && strcmp(e, "warp1") == 0;
+    }();
+    return v;
+}
 
 }  // namespace ncfa
 
@@ -321,14 +423,42 @@ extern "C" int ncfa_onset_strength_batched(const float *d_audio, const int64_t *
         NCFA_LAUNCH_OK("flux_tile_kernel");
         return NCFA_OK;
     }
-    if ((rc = ensure_dynamic_smem((const void *)stft_logmel_kernel, sizeof(OnsetSmem)))) return rc;
     if ((rc = sm_count(&n_sm))) return rc;
-    {
+    if (use_one_frame_form()) {
+        if ((rc = ensure_dynamic_smem((const void *)stft_logmel_kernel, sizeof(OnsetSmem)))) return rc;
         const int64_t groups = ((int64_t)n_seg * frames + kWarps - 1) / kWarps;
         const int grid = (int)(groups < n_sm ? groups : n_sm);  // persistent: one CTA per SM
         ProfScope _p(hop <= 128 ? "stft_logmel_kernel[hop<=128]" : "stft_logmel_kernel[hop>128]", st);
         stft_logmel_kernel<<<grid, kThreads, sizeof(OnsetSmem), st>>>(d_audio, d_seg_off, d_seg_len, n_seg, hop, frames, tb,
                                                                   S, seg_max);
+    } else {
+        // as many warps as the 227 KB of shared memory hold (12 at 22 050 Hz: 95 mel-weight rows)
+        static const int env_warps = [] {
+            const char *e = getenv("NCFA_STFT_WARPS");
+            return e ? atoi(e) : 0;
+        }();
+        const size_t fixed = onset2_fixed_bytes(tb.mel_wt_rows);
+        int warps = (int)((232448 - fixed) / kScrBytes2);
+        if (warps > kWarps2Max) warps = kWarps2Max;
+        if (env_warps >= 1 && env_warps < warps) warps = env_warps;
+        NCFA_REQUIRE(warps >= 1, "mel table too large for shared memory");
+        const size_t smem = fixed + (size_t)warps * kScrBytes2;
+        const int64_t groups = ((int64_t)n_seg * ((frames + 1) / 2) + warps - 1) / warps;
+        const int grid = (int)(groups < n_sm ? groups : n_sm);  // persistent: one CTA per SM
+        ProfScope _p(hop <= 128 ? "stft_logmel_kernel[hop<=128]" : "stft_logmel_kernel[hop>128]", st);
+        if (hop == 64) {
+            if ((rc = ensure_dynamic_smem((const void *)stft_logmel2_kernel<1>, smem))) return rc;
+            stft_logmel2_kernel<1><<<grid, warps * 32, smem, st>>>(d_audio, d_seg_off, d_seg_len, n_seg, hop, frames, tb, S,
+                                                                 seg_max);
+        } else if (hop == 512) {
+            if ((rc = ensure_dynamic_smem((const void *)stft_logmel2_kernel<8>, smem))) return rc;
+            stft_logmel2_kernel<8><<<grid, warps * 32, smem, st>>>(d_audio, d_seg_off, d_seg_len, n_seg, hop, frames, tb, S,
+                                                                 seg_max);
+        } else {
+            if ((rc = ensure_dynamic_smem((const void *)stft_logmel2_kernel<0>, smem))) return rc;
+            stft_logmel2_kernel<0><<<grid, warps * 32, smem, st>>>(d_audio, d_seg_off, d_seg_len, n_seg, hop, frames, tb, S,
+                                                                 seg_max);
+        }
     }
     NCFA_LAUNCH_OK("stft_logmel_kernel");
     const int pad = 1 + NCFA_N_FFT / (2 * hop);

@@ -6,12 +6,22 @@
 // The reference is NOT FFT based: the observable result is the argmax on the
 // strided candidate grid, so that grid is what is evaluated here.
 //
-// This family is memory bound (0.5 flop/B).  Each B sample belongs to up to win/stride = 4
-// candidates and each wa sample to every candidate of its window; kernel 1 gives one CTA one
-// (window, candidate) pair and leaves that reuse to the 126 MB L2 (a pair's whole search span
-// is < 10 MB), so HBM sees every sample once.  Sums are float64 (the float32 inputs are exact in
-// float64; the reference's float32 BLAS sums differ from these by rounding only).
+// This family is memory bound (0.5 flop/B).  The reference's stride is win // 4 (xcorr.py:104), so
+// the search span of a window is a run of stride-long BLOCKS of B and candidate j is blocks
+// j .. j+3 (plus a tail of win − 4·stride <= 3 samples): with D[q][m] = <A block q, B block m> and
+// S[m] = ‖B block m‖²,
+//     dot(wa, wb_j) = D[0][j] + D[1][j+1] + D[2][j+2] + D[3][j+3] (+ tail),   ‖wb_j‖² = S[j] + ... + S[j+3] (+ tail).
+// xcorr_blocks_kernel gives a CTA one window and kBlocksPerCta consecutive B blocks; a thread walks the
+// sample index i (coalesced), keeps the partial sums of its blocks in registers and loads the four A
+// samples of index i once for all of them — every B sample is read from HBM/L2 ONCE and used in five
+// float64 FMAs, every A sample once per CTA of its window (L2).  xcorr_pick_kernel adds the partials in
+// a fixed order (deterministic) and scans the candidates.  Sums are float64 (the float32 inputs are
+// exact in float64; the reference's float32 BLAS sums differ from these by rounding only).
+// The general (win, stride) case of the C ABI — more than 4 blocks per window — keeps the direct
+// kernel (one CTA per (window, candidate)).
+#include <stdlib.h>
 #include "ncfa_common.cuh"
+#include "tc05.cuh"
 
 namespace ncfa {
 
@@ -75,6 +85,314 @@ __global__ void __launch_bounds__(kXcThreads) xcorr_dots_kernel(const float *__r
     if (threadIdx.x == 0) {
         dots[(size_t)w * max_cand + j] = d;
         nb2[(size_t)w * max_cand + j] = q;
+    }
+}
+
+// ---- block form: stride-long blocks of B, nq = win / stride <= 4 of them per candidate ----------------------------------
+constexpr int kBlocksPerCta = 4;   // B blocks whose partial sums one thread keeps (4 × 5 float64 accumulators)
+constexpr int kMaxPieces = 4;      // A blocks per window (win / stride)
+
+// grid (ceil(max_blocks / kBlocksPerCta), n_windows).  part[w][q][m] (q < nq) = <A block q, B block m>,
+// part[w][kMaxPieces][m] = ‖B block m‖²;  na2[w] = ‖wa‖² (from the CTA of blockIdx.x == 0).
+template <int NQ>
+__global__ void __launch_bounds__(kXcThreads) xcorr_blocks_kernel(const float *__restrict__ a, const float *__restrict__ b,
+                                                                   const int64_t *__restrict__ a_pos,
+                                                                   const int64_t *__restrict__ b_lo,
+                                                                   const int32_t *__restrict__ n_cand, int max_blocks,
+                                                                   int win, int stride, double *__restrict__ part,
+                                                                   double *__restrict__ na2) {
+    __shared__ double sh[kXcThreads / 32];
+    const int w = blockIdx.y;
+    const int nc = n_cand[w];
+    if (nc <= 0 && blockIdx.x != 0) return;
+    const int n_blocks = nc > 0 ? nc + NQ - 1 : 0;       // blocks that belong to at least one candidate
+    const int m0 = blockIdx.x * kBlocksPerCta;
+    if (m0 >= n_blocks && blockIdx.x != 0) return;
+    const float *wa = a + a_pos[w];
+    const float *wb = b + b_lo[w] + (int64_t)m0 * stride;
+    const int live = max(0, min(kBlocksPerCta, n_blocks - m0));
+    double d[kBlocksPerCta][NQ], s2[kBlocksPerCta], sa = 0.0;
+#pragma unroll
+    for (int g = 0; g < kBlocksPerCta; ++g) {
+        s2[g] = 0.0;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) d[g][q] = 0.0;
+    }
+    if (live == kBlocksPerCta) {
+        for (int i = threadIdx.x; i < stride; i += kXcThreads) {
+            double x[NQ], y[kBlocksPerCta];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) x[q] = (double)__ldg(wa + (int64_t)q * stride + i);
+#pragma unroll
+            for (int g = 0; g < kBlocksPerCta; ++g) y[g] = (double)__ldg(wb + (int64_t)g * stride + i);
+#pragma unroll
+            for (int g = 0; g < kBlocksPerCta; ++g) {
+                s2[g] = fma(y[g], y[g], s2[g]);
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) d[g][q] = fma(x[q], y[g], d[g][q]);
+            }
+            if (blockIdx.x == 0) {
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) sa = fma(x[q], x[q], sa);
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < stride; i += kXcThreads) {
+            double x[NQ];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) x[q] = (double)__ldg(wa + (int64_t)q * stride + i);
+#pragma unroll
+            for (int g = 0; g < kBlocksPerCta; ++g) {
+                if (g < live) {
+                    const double y = (double)__ldg(wb + (int64_t)g * stride + i);
+                    s2[g] = fma(y, y, s2[g]);
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) d[g][q] = fma(x[q], y, d[g][q]);
+                }
+            }
+            if (blockIdx.x == 0) {
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) sa = fma(x[q], x[q], sa);
+            }
+        }
+    }
+    double *pw = part + (size_t)w * (kMaxPieces + 1) * max_blocks;
+#pragma unroll
+    for (int g = 0; g < kBlocksPerCta; ++g) {
+        if (g < live) {  // CTA-uniform
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const double v = block_sum_256(d[g][q], sh);
+                if (threadIdx.x == 0) pw[(size_t)q * max_blocks + m0 + g] = v;
+            }
+            const double v = block_sum_256(s2[g], sh);
+            if (threadIdx.x == 0) pw[(size_t)kMaxPieces * max_blocks + m0 + g] = v;
+        }
+    }
+    if (blockIdx.x == 0) {
+        // the tail samples [NQ·stride, win) of wa belong to ‖wa‖² too
+        for (int i = NQ * stride + threadIdx.x; i < win; i += kXcThreads) {
+            const double x = (double)__ldg(wa + i);
+            sa = fma(x, x, sa);
+        }
+        sa = block_sum_256(sa, sh);
+        if (threadIdx.x == 0) na2[w] = sa;
+    }
+}
+
+// ---- the same block form fed by the TMA engine ------------------------------------------------------------------------
+// The register form above keeps 8 scalar loads per thread in flight — 16 KB per SM at two CTAs of 84 registers — and
+// stalls on them (ncu: long_scoreboard 15.6 per issue, DRAM at 1.1 TB/s).  Here one thread per CTA streams the four A
+// blocks and the CTA's four B blocks through a 3-stage ring of shared-memory tiles with 1-D bulk async copies
+// (cp.async.bulk + mbarrier complete_tx: ~130 KB in flight per SM, independent of occupancy) and the 256 threads only
+// do shared-memory loads and float64 FMAs.  Blocks start at arbitrary sample offsets, bulk copies need 16-byte
+// alignment: a tile is the aligned superset of its chunk (start rounded down, length rounded up to 16 B — the buffers
+// must be readable up to the next 16-byte boundary, as every cudaMalloc'ed allocation is) and is read at an offset.
+constexpr int kXbChunk = 1024;                 // samples of a block per stage
+constexpr int kXbStages = 3;
+constexpr int kXbTileFloats = kXbChunk + 8;    // chunk + alignment slack, multiple of 4
+
+template <int NQ>
+struct XbSmem {
+    float tile[kXbStages][NQ + kBlocksPerCta][kXbTileFloats];
+    uint64_t full[kXbStages];
+};
+
+template <int NQ>
+__global__ void __launch_bounds__(kXcThreads) xcorr_blocks_tma_kernel(const float *__restrict__ a,
+                                                                       const float *__restrict__ b,
+                                                                       const int64_t *__restrict__ a_pos,
+                                                                       const int64_t *__restrict__ b_lo,
+                                                                       const int32_t *__restrict__ n_cand, int max_blocks,
+                                                                       int win, int stride, double *__restrict__ part,
+                                                                       double *__restrict__ na2) {
+    using namespace tc05;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    XbSmem<NQ> &sm = *reinterpret_cast<XbSmem<NQ> *>(smem_raw);
+    __shared__ double sh[kXcThreads / 32];
+    const int w = blockIdx.y;
+    const int nc = n_cand[w];
+    if (nc <= 0 && blockIdx.x != 0) return;
+    const int n_blocks = nc > 0 ? nc + NQ - 1 : 0;
+    const int m0 = blockIdx.x * kBlocksPerCta;
+    if (m0 >= n_blocks && blockIdx.x != 0) return;
+    const float *wa = a + a_pos[w];
+    const float *wb = b + b_lo[w] + (int64_t)m0 * stride;
+    const int live = max(0, min(kBlocksPerCta, n_blocks - m0));
+    const int n_tiles = NQ + live;
+    const int tid = threadIdx.x;
+    // per-tile sample offset inside its aligned superset (the same for every chunk: chunks start at multiples of 1024)
+    int off[NQ + kBlocksPerCta];
+#pragma unroll
+    for (int t = 0; t < NQ + kBlocksPerCta; ++t) {
+        const float *base = t < NQ ? wa + (int64_t)t * stride : wb + (int64_t)(t - NQ) * stride;
+        off[t] = (int)((reinterpret_cast<uintptr_t>(base) & 15u) >> 2);
+    }
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kXbStages; ++s) mbar_init(&sm.full[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const int n_chunks = (stride + kXbChunk - 1) / kXbChunk;
+    auto issue = [&](int c) {  // thread 0 only
+        const int st = c % kXbStages;
+        const int i0 = c * kXbChunk;
+        const int len = min(kXbChunk, stride - i0);
+        uint32_t total = 0;
+        for (int t = 0; t < n_tiles; ++t) {
+            const float *base = t < NQ ? wa + (int64_t)t * stride : wb + (int64_t)(t - NQ) * stride;
+            const int o = (int)((reinterpret_cast<uintptr_t>(base) & 15u) >> 2);
+            total += (uint32_t)((o + len + 3) & ~3) * 4u;
+        }
+        mbar_arrive_expect_tx(&sm.full[st], total);
+        for (int t = 0; t < n_tiles; ++t) {
+            const float *base = t < NQ ? wa + (int64_t)t * stride : wb + (int64_t)(t - NQ) * stride;
+            const int o = (int)((reinterpret_cast<uintptr_t>(base) & 15u) >> 2);
+            bulk_g2s(&sm.tile[st][t][0], base + i0 - o, (uint32_t)((o + len + 3) & ~3) * 4u, &sm.full[st]);
+        }
+    };
+    if (tid == 0)
+        for (int c = 0; c < kXbStages - 1 && c < n_chunks; ++c) issue(c);
+
+    double d[kBlocksPerCta][NQ], s2[kBlocksPerCta], sa = 0.0;
+#pragma unroll
+    for (int g = 0; g < kBlocksPerCta; ++g) {
+        s2[g] = 0.0;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) d[g][q] = 0.0;
+    }
+    for (int c = 0; c < n_chunks; ++c) {
+        // the stage refilled here was consumed in iteration c − 1 (the __syncthreads below orders those reads first)
+        if (tid == 0 && c + kXbStages - 1 < n_chunks) issue(c + kXbStages - 1);
+        const int st = c % kXbStages;
+        mbar_wait_warp(&sm.full[st], (uint32_t)(c / kXbStages) & 1u);
+        const int len = min(kXbChunk, stride - c * kXbChunk);
+        if (live == kBlocksPerCta) {
+#pragma unroll
+            for (int k = 0; k < kXbChunk / kXcThreads; ++k) {
+                const int i = tid + k * kXcThreads;
+                if (i < len) {
+                    double x[NQ], y[kBlocksPerCta];
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) x[q] = (double)sm.tile[st][q][off[q] + i];
+#pragma unroll
+                    for (int g = 0; g < kBlocksPerCta; ++g) y[g] = (double)sm.tile[st][NQ + g][off[NQ + g] + i];
+#pragma unroll
+                    for (int g = 0; g < kBlocksPerCta; ++g) {
+                        s2[g] = fma(y[g], y[g], s2[g]);
+#pragma unroll
+                        for (int q = 0; q < NQ; ++q) d[g][q] = fma(x[q], y[g], d[g][q]);
+                    }
+                    if (blockIdx.x == 0) {
+#pragma unroll
+                        for (int q = 0; q < NQ; ++q) sa = fma(x[q], x[q], sa);
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kXbChunk / kXcThreads; ++k) {
+                const int i = tid + k * kXcThreads;
+                if (i < len) {
+                    double x[NQ];
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) x[q] = (double)sm.tile[st][q][off[q] + i];
+#pragma unroll
+                    for (int g = 0; g < kBlocksPerCta; ++g) {
+                        if (g < live) {
+                            const double y = (double)sm.tile[st][NQ + g][off[NQ + g] + i];
+                            s2[g] = fma(y, y, s2[g]);
+#pragma unroll
+                            for (int q = 0; q < NQ; ++q) d[g][q] = fma(x[q], y, d[g][q]);
+                        }
+                    }
+                    if (blockIdx.x == 0) {
+#pragma unroll
+                        for (int q = 0; q < NQ; ++q) sa = fma(x[q], x[q], sa);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    double *pw = part + (size_t)w * (kMaxPieces + 1) * max_blocks;
+#pragma unroll
+    for (int g = 0; g < kBlocksPerCta; ++g) {
+        if (g < live) {  // CTA-uniform
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const double v = block_sum_256(d[g][q], sh);
+                if (tid == 0) pw[(size_t)q * max_blocks + m0 + g] = v;
+            }
+            const double v = block_sum_256(s2[g], sh);
+            if (tid == 0) pw[(size_t)kMaxPieces * max_blocks + m0 + g] = v;
+        }
+    }
+    if (blockIdx.x == 0) {
+        for (int i = NQ * stride + tid; i < win; i += kXcThreads) {
+            const double x = (double)__ldg(wa + i);
+            sa = fma(x, x, sa);
+        }
+        sa = block_sum_256(sa, sh);
+        if (tid == 0) na2[w] = sa;
+    }
+}
+
+// one warp per window: candidate sums from the block partials (fixed order), then the same gates and scan as below
+__global__ void __launch_bounds__(32) xcorr_pick_blocks_kernel(const float *__restrict__ a, const float *__restrict__ b,
+                                                               const int64_t *__restrict__ a_pos,
+                                                               const int64_t *__restrict__ b_lo,
+                                                               const int32_t *__restrict__ n_cand, int max_blocks, int nq,
+                                                               int win, int stride, double rms_gate,
+                                                               const double *__restrict__ part,
+                                                               const double *__restrict__ na2,
+                                                               int32_t *__restrict__ best_j, double *__restrict__ best_c) {
+    const int w = blockIdx.x;
+    const int lane = threadIdx.x;
+    const int nc = n_cand[w];
+    const double *pw = part + (size_t)w * (kMaxPieces + 1) * max_blocks;
+    const float *wa = a + a_pos[w];
+    const float *wb = b + b_lo[w];
+    const float rms_a = (float)sqrt(na2[w] / (double)win);
+    const float norm_a32 = (float)sqrt(na2[w]);
+    const double norm_a = (double)norm_a32;
+    int bj = -1;
+    double bc = -1.0;  // best_corr starts at -1.0 (xcorr.py:130)
+    if (!((double)rms_a < rms_gate) && !(norm_a < 1e-10)) {
+        for (int j = lane; j < nc; j += 32) {
+            double dot = 0.0, nb2 = 0.0;
+            for (int q = 0; q < nq; ++q) {
+                dot += pw[(size_t)q * max_blocks + j + q];
+                nb2 += pw[(size_t)kMaxPieces * max_blocks + j + q];
+            }
+            for (int i = nq * stride; i < win; ++i) {  // win − nq·stride < stride tail samples (<= 3 on the reference's grid)
+                const double x = (double)__ldg(wa + i), y = (double)__ldg(wb + (int64_t)j * stride + i);
+                dot = fma(x, y, dot);
+                nb2 = fma(y, y, nb2);
+            }
+            const double norm_b = (double)(float)sqrt(nb2);
+            if (norm_b < 1e-10) continue;
+            const double c = (double)(float)dot / (norm_a * norm_b);  // np.dot is float32; float32 / float64 → float64
+            if (c > bc) {
+                bc = c;
+                bj = j;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double oc = __shfl_xor_sync(0xffffffffu, bc, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+        if (oj >= 0 && (bj < 0 || oc > bc || (oc == bc && oj < bj))) {
+            bc = oc;
+            bj = oj;
+        }
+    }
+    if (lane == 0) {
+        const bool keep = bj >= 0 && bc > 0.0;  // xcorr.py:146
+        best_j[w] = keep ? bj : -1;
+        best_c[w] = keep ? bc : 0.0;
     }
 }
 
@@ -255,13 +573,32 @@ __global__ void __launch_bounds__(kXcThreads) align_pick_kernel(const double *__
     }
 }
 
+// NCFA_XCORR_IMPL=regs: the block form with plain register loads instead of the TMA-fed ring (cross-check / before-after)
+static bool xcorr_use_regs() {
+    static const bool v = [] {
+        const char *e = getenv("NCFA_XCORR_IMPL");
+        return e && strcmp(e, "regs") == 0;
+    }();
+    return v;
+}
+// NCFA_XCORR_IMPL=direct forces the one-CTA-per-candidate kernel (cross-check)
+static bool xcorr_force_direct() {
+    static const bool v = [] {
+        const char *e = getenv("NCFA_XCORR_IMPL");
+        return e && strcmp(e, "direct") == 0;
+    }();
+    return v;
+}
+
 }  // namespace ncfa
 
 using namespace ncfa;
 
 extern "C" size_t ncfa_xcorr_workspace_bytes(int n_windows, int max_cand) {
     if (n_windows <= 0 || max_cand <= 0) return 0;
-    return 2 * align_up((size_t)n_windows * max_cand * 8, 256) + align_up((size_t)n_windows * 8, 256);
+    // block form: (kMaxPieces + 1) partial tables of max_cand + kMaxPieces − 1 blocks per window; direct form: 2 tables
+    const size_t blocks = (size_t)max_cand + kMaxPieces - 1;
+    return align_up((size_t)n_windows * (kMaxPieces + 1) * blocks * 8, 256) + align_up((size_t)n_windows * 8, 256);
 }
 
 extern "C" int ncfa_xcorr_search_batched(const float *d_a, const float *d_b, const int64_t *d_a_pos,
@@ -278,6 +615,48 @@ extern "C" int ncfa_xcorr_search_batched(const float *d_a, const float *d_b, con
     }
     cudaStream_t st = (cudaStream_t)stream;
     char *wp = (char *)d_workspace;
+    const int nq = win / stride;
+    // the tail (win − nq·stride samples per candidate) is summed by one lane in the pick kernel: keep it short
+    if (nq >= 1 && nq <= kMaxPieces && win - nq * stride <= 16 && !xcorr_force_direct()) {
+        const int max_blocks = max_cand + kMaxPieces - 1;
+        double *part = (double *)wp;
+        double *na2b = (double *)(wp + align_up((size_t)n_windows * (kMaxPieces + 1) * max_blocks * 8, 256));
+        dim3 g((max_cand + nq - 1 + kBlocksPerCta - 1) / kBlocksPerCta, n_windows);
+        {
+            ProfScope _p("xcorr_blocks_kernel", st);
+            if (xcorr_use_regs()) {
+                switch (nq) {
+                    case 1: xcorr_blocks_kernel<1><<<g, kXcThreads, 0, st>>>(d_a, d_b, d_a_pos, d_b_lo, d_n_cand, max_blocks, win, stride, part, na2b); break;
+                    case 2: xcorr_blocks_kernel<2><<<g, kXcThreads, 0, st>>>(d_a, d_b, d_a_pos, d_b_lo, d_n_cand, max_blocks, win, stride, part, na2b); break;
+                    case 3: xcorr_blocks_kernel<3><<<g, kXcThreads, 0, st>>>(d_a, d_b, d_a_pos, d_b_lo, d_n_cand, max_blocks, win, stride, part, na2b); break;
+                    default: xcorr_blocks_kernel<4><<<g, kXcThreads, 0, st>>>(d_a, d_b, d_a_pos, d_b_lo, d_n_cand, max_blocks, win, stride, part, na2b); break;
+                }
+            } else {
+                int rc = 0;
+#define NCFA_XB_LAUNCH(NQ_)                                                                                             \
+    do {                                                                                                                \
+        if ((rc = ensure_dynamic_smem((const void *)xcorr_blocks_tma_kernel<NQ_>, sizeof(XbSmem<NQ_>)))) return rc;     \
+        xcorr_blocks_tma_kernel<NQ_><<<g, kXcThreads, sizeof(XbSmem<NQ_>), st>>>(d_a, d_b, d_a_pos, d_b_lo, d_n_cand,    \
+                                                                                 max_blocks, win, stride, part, na2b);  \
+    } while (0)
+                switch (nq) {
+                    case 1: NCFA_XB_LAUNCH(1); break;
+                    case 2: NCFA_XB_LAUNCH(2); break;
+                    case 3: NCFA_XB_LAUNCH(3); break;
+                    default: NCFA_XB_LAUNCH(4); break;
+                }
+#undef NCFA_XB_LAUNCH
+            }
+        }
+        NCFA_LAUNCH_OK("xcorr_blocks_kernel");
+        {
+            ProfScope _p("xcorr_pick_kernel", st);
+            xcorr_pick_blocks_kernel<<<n_windows, 32, 0, st>>>(d_a, d_b, d_a_pos, d_b_lo, d_n_cand, max_blocks, nq, win, stride,
+                                                            rms_gate, part, na2b, d_best_j, d_best_c);
+        }
+        NCFA_LAUNCH_OK("xcorr_pick_blocks_kernel");
+        return NCFA_OK;
+    }
     double *dots = (double *)wp;
     wp += align_up((size_t)n_windows * max_cand * 8, 256);
     double *nb2 = (double *)wp;

@@ -382,13 +382,16 @@ class Engine:
         d_pos, d_lo, d_nc = self.to_dev(a_pos.astype(np.int64)), self.to_dev(b_lo.astype(np.int64)), self.to_dev(
             n_cand.astype(np.int32))
         with torch.cuda.device(self.device):
-            need = lib.ncfa_xcorr_workspace_bytes(n_w, max_cand)
-            ws = self.workspace("xcorr", need)
-            check(lib.ncfa_xcorr_search_batched(_ptr(a), _ptr(b), _ptr(d_pos), _ptr(d_lo), _ptr(d_nc), n_w, max_cand,
-                                                int(win), int(stride), float(rms_gate), _ptr(best_j), _ptr(best_c),
-                                                _ptr(ws), ws.numel(), self._stream()),
-                  "ncfa_xcorr_search_batched")
-        self.launches += 2
+            for s in range(0, n_w, MAX_SEGS_PER_CALL):       # the window index is gridDim.y
+                e = min(n_w, s + MAX_SEGS_PER_CALL)
+                need = lib.ncfa_xcorr_workspace_bytes(e - s, max_cand)
+                ws = self.workspace("xcorr", need)
+                check(lib.ncfa_xcorr_search_batched(_ptr(a), _ptr(b), d_pos.data_ptr() + 8 * s, d_lo.data_ptr() + 8 * s,
+                                                    d_nc.data_ptr() + 4 * s, e - s, max_cand, int(win), int(stride),
+                                                    float(rms_gate), best_j.data_ptr() + 4 * s, best_c.data_ptr() + 8 * s,
+                                                    _ptr(ws), ws.numel(), self._stream()),
+                      "ncfa_xcorr_search_batched")
+                self.launches += 2
         return best_j[:n_w], best_c[:n_w]
 
     # ------------------------------------------------------------------ xcorr.py: intro alignment
