@@ -1,6 +1,7 @@
 // Shared helpers for libncfa (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -43,7 +44,9 @@ int ensure_dynamic_smem(const void *func, size_t bytes);
 // SM count of the current device (cached)
 int sm_count(int *out);
 
-// Optional per-kernel timing (ncfa_profile_enable): a ProfScope around a launch records two CUDA events on the launch
+// Every launch site sits in a ProfScope.  It always opens an NVTX range named after the kernel family (header-only
+// NVTX3: a no-op costing one predicted branch unless a tool such as ncu / nsys injected itself), and —
+// optional per-kernel timing (ncfa_profile_enable) — a ProfScope around a launch records two CUDA events on the launch
 // stream (it owns both, so scopes of concurrent host threads never pair up with each other) and hands them to the
 // registry when it closes; ncfa_profile_report() synchronises them and sums per kernel name.
 bool prof_enabled();
@@ -54,6 +57,7 @@ struct ProfScope {
     bool on;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     ProfScope(const char *n, cudaStream_t s) : name(n), st(s), on(prof_enabled()) {
+        nvtxRangePushA(n);
         if (on) {
             on = cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess &&
                  cudaEventRecord(e0, st) == cudaSuccess;
@@ -61,6 +65,7 @@ struct ProfScope {
     }
     ~ProfScope() {
         if (on && cudaEventRecord(e1, st) == cudaSuccess) prof_commit(name, e0, e1);
+        nvtxRangePop();
     }
 };
 
