@@ -127,6 +127,9 @@ __device__ __forceinline__ void warp_power_spectrum_global(const float *__restri
 // warp_power_spectrum_regs (same products, same order), so the spectra are bit-identical.
 template <int K2>
 struct PostStage2 {
+    // Stores 4·|X[k]|²: the two halvings of the un-pack (E = ½(..), O = ½(..)) are exact scalings by a power of two, so
+    // they commute with every rounding below — the caller multiplies the mel sums by ¼ instead (two FMUL2 fewer per
+    // bin pair, bit-identical log-mel values).
     static __device__ __forceinline__ void one(const cf (&v)[32], int lane, cf w, float *pw) {
         cf zk = v[br5(K2)];
         cf own = v[br5((32 - K2) & 31)];
@@ -136,8 +139,8 @@ struct PostStage2 {
         p.x = __shfl_sync(0xffffffffu, snd.x, src);
         p.y = __shfl_sync(0xffffffffu, snd.y, src);
         if (lane == 0) p = own;
-        cf e = cscale(cadd_conj(zk, p), 0.5f);
-        cf o = cscale(cmul_mi(csub_conj(zk, p)), 0.5f);
+        cf e = cadd_conj(zk, p);            // 2E = Z[k] + conj Z[N−k]
+        cf o = cmul_mi(csub_conj(zk, p));   // 2O = (Z[k] − conj Z[N−k]) / i
         cf wo = cmul(o, w);
         cf x = cadd(e, wo);
         cf y = csub(e, wo);
@@ -152,9 +155,9 @@ struct PostStage2 {
         if constexpr (K2 == 0) {
             if (lane == 0) {
                 cf z = a[br5(16)];
-                pa[512] = z.x * z.x + z.y * z.y;
+                pa[512] = 4.0f * (z.x * z.x + z.y * z.y);
                 z = b[br5(16)];
-                pb[512] = z.x * z.x + z.y * z.y;
+                pb[512] = 4.0f * (z.x * z.x + z.y * z.y);
             }
         }
     }

@@ -163,8 +163,9 @@ __global__ void __launch_bounds__(kWarps2Max * 32, 1) stft_logmel2_kernel(const 
                 acca = fmaf(w, ka[i], acca);
                 accb = fmaf(w, kb[i], accb);
             }
-            const float dba = 10.0f * log10f(fmaxf(1e-10f, acca));
-            const float dbb = 10.0f * log10f(fmaxf(1e-10f, accb));
+            // the pair form stores 4·|X|² (stft_core.cuh PostStage2): exact ¼ here
+            const float dba = 10.0f * log10f(fmaxf(1e-10f, 0.25f * acca));
+            const float dbb = 10.0f * log10f(fmaxf(1e-10f, 0.25f * accb));
             const int band = mel_band_of(q, lane);
             Sa[band] = dba;
             vmax = fmaxf(vmax, dba);
