@@ -44,6 +44,9 @@ const char *ncfa_last_error(void);
  * lines into buf, then forgets them. */
 void ncfa_profile_enable(int on);
 int ncfa_profile_report(char *buf, size_t cap);
+/* Same records as a timeline: "name,stream,t0_ms,t1_ms" per launch, relative to the first record (diagnostics:
+ * where concurrent host workers leave the device idle).  Clears the records. */
+int ncfa_profile_timeline(char *buf, size_t cap);
 
 /* Build and upload the constant tables (Hann, FFT twiddles, Slaney mel bank for `sr`) on the
  * current device.  Idempotent and thread-safe; the other entry points call it lazily. */

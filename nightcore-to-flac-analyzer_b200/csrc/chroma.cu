@@ -197,6 +197,19 @@ static void build_halfband(std::vector<double> &h) {
     for (auto &v : h) v /= hs;
 }
 
+// the 64 even taps and the centre tap of the half-band filter also live in constant memory: the decimator's FMAs take
+// them as constant-bank operands (no shared-memory load per tap)
+__constant__ double c_hb_even[64];
+__constant__ double c_hb_mid;
+__constant__ float c_hbf_even[64];
+__constant__ float c_hbf_mid;
+template <typename acc_t> __device__ __forceinline__ acc_t hb_even_tap(int m);
+template <> __device__ __forceinline__ double hb_even_tap<double>(int m) { return c_hb_even[m]; }
+template <> __device__ __forceinline__ float hb_even_tap<float>(int m) { return c_hbf_even[m]; }
+template <typename acc_t> __device__ __forceinline__ acc_t hb_mid_tap();
+template <> __device__ __forceinline__ double hb_mid_tap<double>() { return c_hb_mid; }
+template <> __device__ __forceinline__ float hb_mid_tap<float>() { return c_hbf_mid; }
+
 static std::mutex g_hb_mu;
 static std::map<int, const double *> g_hb;
 int get_halfband_device(const double **out) {
@@ -213,6 +226,20 @@ int get_halfband_device(const double **out) {
     double *dh = nullptr;
     NCFA_CUDA_OK(cudaMalloc(&dh, h.size() * sizeof(double)));
     NCFA_CUDA_OK(cudaMemcpy(dh, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+    {
+        double ev[64];
+        float evf[64];
+        for (int m = 0; m < 64; ++m) {
+            ev[m] = h[2 * m];
+            evf[m] = (float)h[2 * m];
+        }
+        const double mid = h[(kHbTaps - 1) / 2];
+        const float midf = (float)mid;
+        NCFA_CUDA_OK(cudaMemcpyToSymbol(c_hb_even, ev, sizeof(ev)));
+        NCFA_CUDA_OK(cudaMemcpyToSymbol(c_hb_mid, &mid, sizeof(mid)));
+        NCFA_CUDA_OK(cudaMemcpyToSymbol(c_hbf_even, evf, sizeof(evf)));
+        NCFA_CUDA_OK(cudaMemcpyToSymbol(c_hbf_mid, &midf, sizeof(midf)));
+    }
     g_hb[dev] = dh;
     *out = dh;
     return NCFA_OK;
@@ -468,16 +495,18 @@ __global__ void __launch_bounds__(256) tuning_pick_kernel(const int32_t *__restr
 // from a 67-sample register window (17 conflict-free LDS.128), float64 accumulation.
 // Accumulation type: float64 like the oracle.  A float32 variant (NCFA_DECIMATE=f32) was measured: 10.6 -> 8.3 ms per
 // 250 pairs only — the kernel is paced by its strided staging loads, not by the FP64 pipe — so the exact sums stay.
-constexpr int kDecOutPerCta = 1024;
+// ncu (profiles/r2f_ncu_summary.md, 4 outputs per thread): XU pipe 61 % — the float → double conversions of the register
+// window, 17.75 per output — next to FP64 54 %.  Eight outputs per thread share a 71-sample window: 9.9 conversions per
+// output, and the kernel is left with its 64 float64 FMAs per output.
+constexpr int kDecPerThread = 8;
+constexpr int kDecOutPerCta = 256 * kDecPerThread;
 template <typename acc_t>
 __global__ void __launch_bounds__(256) decimate2_kernel(const float *__restrict__ audio,
                                                         const int64_t *__restrict__ seg_off,
                                                         const int32_t *__restrict__ seg_len, int level,
                                                         float *__restrict__ pyr, size_t pyr_stride, size_t in_off,
                                                         size_t out_off, const double *__restrict__ hb) {
-    __shared__ acc_t h_even[64];
-    __shared__ acc_t h_mid;
-    __shared__ __align__(16) float xo[kDecOutPerCta + 64 + 4];
+    __shared__ __align__(16) float xo[kDecOutPerCta + 64 + 8];
     __shared__ __align__(16) float xe[kDecOutPerCta];
     const int seg = blockIdx.y;
     const int n0 = seg_len[seg];
@@ -486,12 +515,10 @@ __global__ void __launch_bounds__(256) decimate2_kernel(const float *__restrict_
     if (o0 >= n_out) return;
     const float *in = (level == 1) ? audio + seg_off[seg] : pyr + (size_t)seg * pyr_stride + in_off;
     float *out = pyr + (size_t)seg * pyr_stride + out_off;
-    if (threadIdx.x < 64) h_even[threadIdx.x] = (acc_t)hb[2 * threadIdx.x];
-    if (threadIdx.x == 64) h_mid = (acc_t)hb[(kHbTaps - 1) / 2];
-    // xo[i] = in[2(o0 − 32 + i) + 1], i < 1024 + 64 + 4;  xe[i] = in[2(o0 + i)], i < 1024: one coalesced float2 load
-    // (even sample, odd sample) feeds both arrays when the level's base is 8-byte aligned
+    // xo[i] = in[2(o0 − 32 + i) + 1], i < kDecOutPerCta + 64 + 8;  xe[i] = in[2(o0 + i)], i < kDecOutPerCta: one coalesced
+    // float2 load (even sample, odd sample) feeds both arrays when the level's base is 8-byte aligned
     if ((reinterpret_cast<uintptr_t>(in) & 7u) == 0) {
-        for (int i = threadIdx.x; i < kDecOutPerCta + 64 + 4; i += 256) {
+        for (int i = threadIdx.x; i < kDecOutPerCta + 64 + 8; i += 256) {
             const int64_t p = 2 * ((int64_t)o0 - 32 + i);
             float2 v = make_float2(0.0f, 0.0f);
             if (p >= 0 && p + 1 < n_in) v = __ldg(reinterpret_cast<const float2 *>(in + p));
@@ -500,7 +527,7 @@ __global__ void __launch_bounds__(256) decimate2_kernel(const float *__restrict_
             if (i >= 32 && i < 32 + kDecOutPerCta) xe[i - 32] = v.x;
         }
     } else {
-        for (int i = threadIdx.x; i < kDecOutPerCta + 64 + 4; i += 256) {
+        for (int i = threadIdx.x; i < kDecOutPerCta + 64 + 8; i += 256) {
             const int64_t p = 2 * ((int64_t)o0 - 32 + i) + 1;
             xo[i] = (p >= 0 && p < n_in) ? __ldg(in + p) : 0.0f;
         }
@@ -510,36 +537,41 @@ __global__ void __launch_bounds__(256) decimate2_kernel(const float *__restrict_
         }
     }
     __syncthreads();
-    const int t = 4 * threadIdx.x;  // outputs o0 + t .. o0 + t + 3 use xo[t .. t + 66]
-    float w[68];
+    const int t = kDecPerThread * threadIdx.x;  // outputs o0 + t .. o0 + t + 7 use xo[t .. t + 70]
+    acc_t w[72];
 #pragma unroll
-    for (int j = 0; j < 17; ++j) {
+    for (int j = 0; j < 18; ++j) {
         const float4 v = *reinterpret_cast<const float4 *>(xo + t + 4 * j);
-        w[4 * j] = v.x;
-        w[4 * j + 1] = v.y;
-        w[4 * j + 2] = v.z;
-        w[4 * j + 3] = v.w;
+        w[4 * j] = (acc_t)v.x;
+        w[4 * j + 1] = (acc_t)v.y;
+        w[4 * j + 2] = (acc_t)v.z;
+        w[4 * j + 3] = (acc_t)v.w;
     }
-    const float4 e = *reinterpret_cast<const float4 *>(xe + t);
-    acc_t a0 = h_mid * (acc_t)e.x, a1 = h_mid * (acc_t)e.y, a2 = h_mid * (acc_t)e.z, a3 = h_mid * (acc_t)e.w;
+    acc_t a[kDecPerThread];
+    {
+        const float4 e0 = *reinterpret_cast<const float4 *>(xe + t);
+        const float4 e1 = *reinterpret_cast<const float4 *>(xe + t + 4);
+        const acc_t hm = hb_mid_tap<acc_t>();
+        a[0] = hm * (acc_t)e0.x, a[1] = hm * (acc_t)e0.y, a[2] = hm * (acc_t)e0.z, a[3] = hm * (acc_t)e0.w;
+        a[4] = hm * (acc_t)e1.x, a[5] = hm * (acc_t)e1.y, a[6] = hm * (acc_t)e1.z, a[7] = hm * (acc_t)e1.w;
+    }
 #pragma unroll
-    for (int m = 0; m < 64; ++m) {
-        const acc_t hm = h_even[m];
-        a0 = fma(hm, (acc_t)w[m], a0);
-        a1 = fma(hm, (acc_t)w[m + 1], a1);
-        a2 = fma(hm, (acc_t)w[m + 2], a2);
-        a3 = fma(hm, (acc_t)w[m + 3], a3);
+    for (int m = 0; m < 64; ++m) {  // ascending m per output, as before: the sums round identically
+        const acc_t hm = hb_even_tap<acc_t>(m);  // compile-time index: a constant-bank operand of the FMAs
+#pragma unroll
+        for (int u = 0; u < kDecPerThread; ++u) a[u] = fma(hm, w[m + u], a[u]);
     }
     const acc_t r2 = (acc_t)1.4142135623730951;
     const int o = o0 + t;
-    if (o + 3 < n_out && (reinterpret_cast<uintptr_t>(out + o) & 15u) == 0) {  // level offsets are multiples of 4 floats
+    if (o + kDecPerThread - 1 < n_out && (reinterpret_cast<uintptr_t>(out + o) & 15u) == 0) {  // level offsets: multiples of 4 floats
         *reinterpret_cast<float4 *>(out + o) =
-            make_float4((float)(a0 * r2), (float)(a1 * r2), (float)(a2 * r2), (float)(a3 * r2));
+            make_float4((float)(a[0] * r2), (float)(a[1] * r2), (float)(a[2] * r2), (float)(a[3] * r2));
+        *reinterpret_cast<float4 *>(out + o + 4) =
+            make_float4((float)(a[4] * r2), (float)(a[5] * r2), (float)(a[6] * r2), (float)(a[7] * r2));
     } else {
-        if (o < n_out) out[o] = (float)(a0 * r2);
-        if (o + 1 < n_out) out[o + 1] = (float)(a1 * r2);
-        if (o + 2 < n_out) out[o + 2] = (float)(a2 * r2);
-        if (o + 3 < n_out) out[o + 3] = (float)(a3 * r2);
+#pragma unroll
+        for (int u = 0; u < kDecPerThread; ++u)
+            if (o + u < n_out) out[o + u] = (float)(a[u] * r2);
     }
 }
 
@@ -740,10 +772,12 @@ constexpr int kTcAccCol0 = kTcAStages * kTcACols;        // 320
 constexpr int kTcAccN = kTcN;                            // accumulator columns (80: 36 real, 36 imaginary, 8 pad)
 constexpr int kTcTmemCols = 512;                         // 320 (A ring) + 2 × 80 (accumulators)
 constexpr int kTcAPre = 4;                               // k-tiles of A rows in flight (cp.async ring in shared memory)
+constexpr int kTcAPlane = kTcFrames + 1;                 // float4 per chunk plane of the A staging ring
 
 struct TcSmem {
     alignas(1024) unsigned char b[kTcBStages][kTcBStageBytes];
-    float4 arow[kTcAPre][8][kTcFrames];  // [slot][16-byte chunk][frame]: conflict-free for cp.async and LDS.128
+    float4 arow[kTcAPre][8 * kTcAPlane];  // [slot][16-byte chunk · kTcAPlane + frame]: the odd plane stride keeps both the
+                                          // (8 rows × 4 chunks) cp.async writes and the per-row LDS.128 reads conflict free
     float chroma_part[kTcFrames][16];    // [frame][4·q + j]: partial chroma (3q + j) mod 12 of column quarter q
     alignas(8) uint64_t full_a[kTcAStages], empty_a[kTcAStages], full_b[kTcBStages], empty_b[kTcBStages];
     uint64_t acc_full[2], acc_empty[2];
@@ -791,14 +825,17 @@ __device__ __forceinline__ void tc_epilogue_quarter(uint32_t acc_addr, float (&p
     }
 }
 
+// DBG = false is the production instantiation (the timing-experiment switches compile away); DBG = true honours `dbg`.
+template <bool DBG>
 __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__restrict__ audio,
                                                                const int64_t *__restrict__ seg_off,
                                                                const int32_t *__restrict__ seg_len,
                                                                const float *__restrict__ pyr, PyrOffsets po,
                                                                const int32_t *__restrict__ tuning_idx,
                                                                const float *__restrict__ Bimg, int tile_stride,
-                                                               double *__restrict__ partial, int dbg) {
+                                                               double *__restrict__ partial, int dbg_arg) {
     using namespace tc05;
+    const int dbg = DBG ? dbg_arg : 0;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     TcSmem &sm = *reinterpret_cast<TcSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int seg = blockIdx.y;
@@ -874,50 +911,55 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
         // comes from the src-size (zfill) form — row starts are multiples of 4 samples, so a chunk never straddles 0.
         // The per-tile address arithmetic is kept to a handful of 32-bit operations: this instruction stream, not the
         // MMAs or the memory system, is what paces the kernel (NCFA_TC_DEBUG timing experiments).
+        // The global side of the copies is coalesced: per cp.async instruction the warp's lanes (r8 = lane >> 2, c = lane & 3)
+        // fetch the four 16-byte chunks (column half q) of EIGHT rows — 64 contiguous bytes per row — instead of one
+        // chunk of 32 different rows (32 different cache lines per instruction at the upper octaves: the L1 tag stage,
+        // not the tensor pipe, paced the kernel — profiles/r2f_ncu_summary.md, l1tex 65 % busy).  Four instructions
+        // j = 0..3 cover the warp's 32 rows (row 8j + r8).
         constexpr int kChunks = kTcVals / 4;
+        static_assert(kChunks == 4, "lane mapping below assumes 4 chunks per row half");
         const float *y0 = audio + seg_off[seg];
         const bool y0_aligned = (reinterpret_cast<uintptr_t>(y0) & 15u) == 0;
-        const float *yrow = nullptr;  // this thread's row start + its column offset, for the octave being issued
-        int neg_lim = 0, lim = 0;     // valid sample offsets p of the row satisfy neg_lim <= p < lim
+        const float *y0_down = reinterpret_cast<const float *>(reinterpret_cast<uintptr_t>(y0) & ~uintptr_t(15));
+        const int r8 = lane >> 2, cc = lane & 3;
+        const float *ylev = nullptr;  // level base of the octave being issued
+        int row0 = 0, row_step = 0, len_o = 0;  // sample offset of (row 32rg + r8, chunk 4q + cc) at k-tile 0; 8·hop; level length
         bool oct_async = true;
         auto issue = [&](int it) {
             const int kt = ((it & 31) + kshift) & 31;
             if ((it & 31) == 0) {  // new octave: row geometry
                 const int o = it >> 5;
                 const int hop = 512 >> o;
-                const float *y = (o == 0) ? y0 : pseg + po.off[o];
-                const int len = level_len(n, o);
-                const int64_t row = (int64_t)(t0 + f) * hop - kCqtNfft / 2 + kTcVals * q;
-                yrow = y + row;
-                neg_lim = row < 0 ? (int)(-row) : 0;
-                const int64_t l64 = (int64_t)len - row;
-                lim = l64 < 0 ? 0 : (l64 > 0x3fffffff ? 0x3fffffff : (int)l64);
+                ylev = (o == 0) ? y0 : pseg + po.off[o];
+                len_o = level_len(n, o);
+                row0 = (t0 + 32 * rg + r8) * hop - kCqtNfft / 2 + kTcVals * q + 4 * cc;
+                row_step = 8 * hop;
                 oct_async = (o > 0) || y0_aligned;
             }
-            float4 *slot = &sm.arow[it % kTcAPre][kChunks * q][f];
-            const int p0 = kt * kTcKT;
-            if (dbg & 2) {  // timing experiment: no A traffic
+            float4 *slot = &sm.arow[it % kTcAPre][(kChunks * q + cc) * kTcAPlane + 32 * rg + r8];
+            const int p0 = row0 + kt * kTcKT;
+            if (DBG && (dbg & 2)) {  // timing experiment: no A traffic
             } else if (oct_async) {
 #pragma unroll
-                for (int c = 0; c < kChunks; ++c) {
-                    const int p = p0 + 4 * c;
-                    const int rem = (lim - p) * 4;
-                    const uint32_t bytes = (p < neg_lim || rem <= 0) ? 0u : (uint32_t)(rem > 16 ? 16 : rem);
-                    const float *src = bytes ? yrow + p : y0;
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(slot + c * kTcFrames)),
-                                 "l"(src), "r"(bytes)
+                for (int j = 0; j < 4; ++j) {
+                    const int p = p0 + j * row_step;  // first sample of this 16-byte piece (multiple of 4: never straddles 0)
+                    const int rem = (len_o - p) * 4;
+                    const uint32_t bytes = (p < 0 || rem <= 0) ? 0u : (uint32_t)(rem > 16 ? 16 : rem);
+                    const float *src = bytes ? ylev + p : y0_down;  // src-size 0: nothing is read, but the address stays aligned
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(slot + 8 * j)), "l"(src),
+                                 "r"(bytes)
                                  : "memory");
                 }
-            } else {  // unaligned first level (arbitrary caller offset): plain loads into the same slot
+            } else {  // unaligned first level (arbitrary caller offset): plain loads into the same slots
 #pragma unroll
-                for (int c = 0; c < kChunks; ++c) {
+                for (int j = 0; j < 4; ++j) {
                     float xr[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const int p = p0 + 4 * c + i;
-                        xr[i] = (p >= neg_lim && p < lim) ? __ldg(yrow + p) : 0.0f;
+                        const int p = p0 + j * row_step + i;
+                        xr[i] = (p >= 0 && p < len_o) ? __ldg(ylev + p) : 0.0f;
                     }
-                    slot[c * kTcFrames] = make_float4(xr[0], xr[1], xr[2], xr[3]);
+                    slot[8 * j] = make_float4(xr[0], xr[1], xr[2], xr[3]);
                 }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
@@ -928,14 +970,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
             if (it + kTcAPre - 1 < kIters) issue(it + kTcAPre - 1);
             else asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group %0;" ::"n"(kTcAPre - 1) : "memory");
+            __syncwarp();  // the row this thread reads was fetched by other lanes of its warp
             const int o = it >> 5, kt = it & 31;
             const int st = it % kTcAStages;
             uint32_t h[kTcVals], l[kTcVals];
             {
-                const float4 *slot = &sm.arow[it % kTcAPre][kChunks * q][f];
+                const float4 *slot = &sm.arow[it % kTcAPre][(kChunks * q) * kTcAPlane + f];
 #pragma unroll
                 for (int c = 0; c < kChunks; ++c) {
-                    const float4 v = slot[c * kTcFrames];
+                    const float4 v = slot[c * kTcAPlane];
                     const float x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -945,8 +988,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
                     }
                 }
             }
+            __syncwarp();  // all lanes have read the slot before other lanes re-fill it (issue() of the next iteration)
             if (pending) {  // publish the PREVIOUS tile: its tcgen05.st had a whole iteration to land
-                if (!(dbg & 8)) wait_st();
+                if (!(DBG && (dbg & 8))) wait_st();
                 fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.full_a[(it - 1) % kTcAStages]);
@@ -958,7 +1002,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
             tmem_st_vals(a0 + kTcKT, l);
             pending = true;
             if (kt == kKTiles - 1) {  // octave boundary (and the very last tile): publish before the epilogue
-                if (!(dbg & 8)) wait_st();
+                if (!(DBG && (dbg & 8))) wait_st();
                 fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.full_a[st]);
@@ -1021,7 +1065,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
 #pragma unroll
                     for (int k = 0; k < kTcKT / 8; ++k) {
                         const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 32 bytes per K = 8 step inside the swizzle row
-                        if (dbg & 4) continue;  // timing experiment: no MMAs
+                        if (DBG && (dbg & 4)) continue;  // timing experiment: no MMAs
                         mma_tf32_ts(d, ah + 8 * k, bh + adv, idesc, (kt | k) != 0);  // 3×TF32: Ah·Bh + Al·Bh + Ah·Bl
                         mma_tf32_ts(d, al + 8 * k, bh + adv, idesc, 1);
                         mma_tf32_ts(d, ah + 8 * k, bl + adv, idesc, 1);
@@ -1040,7 +1084,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
             const int sb = it % kTcBStages, kt = ((it % kKTiles) + kshift) & (kKTiles - 1);
             mbar_wait_warp(&sm.empty_a[sb], (uint32_t)(((it / kTcBStages) & 1) ^ 1), 100);
             if (elect_one()) {
-                if ((dbg & 1) && it >= kTcBStages) {  // timing experiment: no B traffic after the first ring fill
+                if (DBG && (dbg & 1) && it >= kTcBStages) {  // timing experiment: no B traffic after the first ring fill
                     mbar_arrive(&sm.full_b[sb]);
                 } else {
                     mbar_arrive_expect_tx(&sm.full_b[sb], kTcBStageBytes);
@@ -1209,7 +1253,8 @@ extern "C" int ncfa_chroma_mean_batched(const float *d_audio, const int64_t *d_s
         use_tc = (e && strcmp(e, "simt") == 0) ? 0 : 1;
     }
     if ((rc = ensure_dynamic_smem((const void *)cqt_chroma_kernel, sizeof(CqtSmem)))) return rc;
-    if ((rc = ensure_dynamic_smem((const void *)cqt_tc_kernel, sizeof(TcSmem) + 1024))) return rc;
+    if ((rc = ensure_dynamic_smem((const void *)cqt_tc_kernel<false>, sizeof(TcSmem) + 1024))) return rc;
+    if ((rc = ensure_dynamic_smem((const void *)cqt_tc_kernel<true>, sizeof(TcSmem) + 1024))) return rc;
     const int tiles = chroma_tiles(max_seg_len);  // partial[] stride (sized for the 32-frame tiles of the SIMT kernel)
     if (use_tc) {
         ProfScope _p("cqt_tc_kernel", st);
@@ -1219,8 +1264,12 @@ extern "C" int ncfa_chroma_mean_batched(const float *d_audio, const int64_t *d_s
             const char *e = getenv("NCFA_TC_DEBUG");  // timing experiments only (results are wrong when non-zero)
             dbg = e ? atoi(e) : 0;
         }
-        cqt_tc_kernel<<<g, kTcThreads, sizeof(TcSmem) + 1024, st>>>(d_audio, d_seg_off, d_seg_len, pyr, po, d_tuning_idx,
-                                                                    ct.Bimg, tiles, partial, dbg);
+        if (dbg)
+            cqt_tc_kernel<true><<<g, kTcThreads, sizeof(TcSmem) + 1024, st>>>(d_audio, d_seg_off, d_seg_len, pyr, po,
+                                                                              d_tuning_idx, ct.Bimg, tiles, partial, dbg);
+        else
+            cqt_tc_kernel<false><<<g, kTcThreads, sizeof(TcSmem) + 1024, st>>>(d_audio, d_seg_off, d_seg_len, pyr, po,
+                                                                               d_tuning_idx, ct.Bimg, tiles, partial, 0);
         NCFA_LAUNCH_OK("cqt_tc_kernel");
     } else {
         ProfScope _p("cqt_chroma_kernel", st);

@@ -55,15 +55,16 @@ int sm_count(int *out) {
 struct ProfEntry {
     const char *name;
     cudaEvent_t e0, e1;
+    cudaStream_t st;
 };
 static std::mutex g_prof_mu;
 static bool g_prof_on = false;
 static std::vector<ProfEntry> g_prof;
 
 bool prof_enabled() { return g_prof_on; }
-void prof_commit(const char *name, cudaEvent_t e0, cudaEvent_t e1) {
+void prof_commit(const char *name, cudaEvent_t e0, cudaEvent_t e1, cudaStream_t st) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
-    g_prof.push_back(ProfEntry{name, e0, e1});
+    g_prof.push_back(ProfEntry{name, e0, e1, st});
 }
 
 // ---- Slaney mel scale (librosa.filters.mel(htk=False, norm='slaney'))
@@ -342,6 +343,36 @@ extern "C" int ncfa_profile_report(char *buf, size_t cap) {
     size_t n = out.size() < cap - 1 ? out.size() : cap - 1;
     memcpy(buf, out.data(), n);
     buf[n] = 0;
+    return NCFA_OK;
+}
+// "name,stream,t0_ms,t1_ms\n" per recorded launch (times relative to the first record's start), written into buf;
+// clears the records.  Diagnostic companion of ncfa_profile_report: shows where the streams of concurrent host workers
+// leave the device idle.
+extern "C" int ncfa_profile_timeline(char *buf, size_t cap) {
+    using namespace ncfa;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (cap == 0) return NCFA_E_INVALID;
+    std::string out;
+    char line[256];
+    cudaEvent_t base = g_prof.empty() ? nullptr : g_prof[0].e0;
+    if (base) cudaEventSynchronize(base);
+    for (auto &e : g_prof) {
+        float t0 = 0.f, t1 = 0.f;
+        if (cudaEventSynchronize(e.e1) == cudaSuccess && cudaEventElapsedTime(&t0, base, e.e0) == cudaSuccess &&
+            cudaEventElapsedTime(&t1, base, e.e1) == cudaSuccess) {
+            snprintf(line, sizeof(line), "%s,%p,%.4f,%.4f\n", e.name, (void *)e.st, t0, t1);
+            if (out.size() + strlen(line) + 1 < cap) out += line;
+        } else {
+            (void)cudaGetLastError();
+        }
+    }
+    for (auto &e : g_prof) {
+        cudaEventDestroy(e.e0);
+        cudaEventDestroy(e.e1);
+    }
+    g_prof.clear();
+    memcpy(buf, out.data(), out.size());
+    buf[out.size()] = 0;
     return NCFA_OK;
 }
 extern "C" const char *ncfa_last_error(void) { return ncfa::g_err; }

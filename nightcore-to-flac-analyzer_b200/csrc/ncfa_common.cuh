@@ -50,7 +50,7 @@ int sm_count(int *out);
 // stream (it owns both, so scopes of concurrent host threads never pair up with each other) and hands them to the
 // registry when it closes; ncfa_profile_report() synchronises them and sums per kernel name.
 bool prof_enabled();
-void prof_commit(const char *name, cudaEvent_t e0, cudaEvent_t e1);
+void prof_commit(const char *name, cudaEvent_t e0, cudaEvent_t e1, cudaStream_t st);
 struct ProfScope {
     const char *name;
     cudaStream_t st;
@@ -64,7 +64,7 @@ struct ProfScope {
         }
     }
     ~ProfScope() {
-        if (on && cudaEventRecord(e1, st) == cudaSuccess) prof_commit(name, e0, e1);
+        if (on && cudaEventRecord(e1, st) == cudaSuccess) prof_commit(name, e0, e1, st);
         nvtxRangePop();
     }
 };

@@ -339,6 +339,188 @@ __global__ void __launch_bounds__(kXcThreads) xcorr_blocks_tma_kernel(const floa
     }
 }
 
+// ---- ring form (the default): the same tiles through a ring with full / empty mbarriers and a producer warp ------------
+// ncu on the kernel above (profiles/r2f_ncu_summary.md): FP64 pipe 20 %, XU (float → double conversions) 28 %, and a third
+// of all stall samples sit behind the per-chunk __syncthreads: warp 0's single lane walks the eight tiles twice (byte
+// count, then the copies — a serial ~1000-cycle path, longer than the chunk's arithmetic), and everybody waits for it.
+// Here nothing is CTA-wide inside the loop: the last warp only produces (lane t owns tile t: eight lanes issue the eight
+// bulk copies of a stage in parallel, from pointers computed once), the other warps only consume (wait full → shared
+// loads + float64 FMAs → one arrive per warp on the stage's empty barrier).  A first version with 512-sample chunks
+// (2 KB copies, six stages, two CTAs per SM) ran at 1.5 TB/s against 2.6 TB/s for the 4 KB copies above: the SM's copy
+// engine spends a fixed ~200 cycles per bulk copy at these 16-byte-aligned addresses, so bytes per copy set the rate —
+// hence 2048-sample chunks (8 KB copies), three stages (197 KB), one CTA of 16 consumer warps per SM.
+constexpr int kXrChunk = 2048;
+constexpr int kXrStages = 3;
+constexpr int kXrTileFloats = kXrChunk + 8;
+constexpr int kXrConsumers = 512;                   // 16 consumer warps
+constexpr int kXrThreads = kXrConsumers + 32;       // + the producer warp
+
+template <int NQ>
+struct XrSmem {
+    float tile[kXrStages][NQ + kBlocksPerCta][kXrTileFloats];
+    uint64_t full[kXrStages], empty[kXrStages];
+};
+
+// block sum over the consumer threads (named barrier 1: the producer warp is not part of it)
+__device__ __forceinline__ double consumer_sum_256(double v, double *sh) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    asm volatile("bar.sync 1, %0;" ::"n"(kXrConsumers) : "memory");
+    double s = 0.0;
+    if (threadIdx.x == 0) {
+        for (int w = 0; w < kXrConsumers / 32; ++w) s += sh[w];
+        sh[0] = s;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kXrConsumers) : "memory");
+    s = sh[0];
+    asm volatile("bar.sync 1, %0;" ::"n"(kXrConsumers) : "memory");
+    return s;
+}
+
+template <int NQ>
+__global__ void __launch_bounds__(kXrThreads, 1) xcorr_blocks_ring_kernel(const float *__restrict__ a,
+                                                                       const float *__restrict__ b,
+                                                                       const int64_t *__restrict__ a_pos,
+                                                                       const int64_t *__restrict__ b_lo,
+                                                                       const int32_t *__restrict__ n_cand, int max_blocks,
+                                                                       int win, int stride, double *__restrict__ part,
+                                                                       double *__restrict__ na2) {
+    using namespace tc05;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    XrSmem<NQ> &sm = *reinterpret_cast<XrSmem<NQ> *>(smem_raw);
+    __shared__ double sh[kXrConsumers / 32];
+    const int w = blockIdx.y;
+    const int nc = n_cand[w];
+    if (nc <= 0 && blockIdx.x != 0) return;
+    const int n_blocks = nc > 0 ? nc + NQ - 1 : 0;
+    const int m0 = blockIdx.x * kBlocksPerCta;
+    if (m0 >= n_blocks && blockIdx.x != 0) return;
+    const float *wa = a + a_pos[w];
+    const float *wb = b + b_lo[w] + (int64_t)m0 * stride;
+    const int live = max(0, min(kBlocksPerCta, n_blocks - m0));
+    const int n_tiles = NQ + live;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kXrStages; ++s) {
+            mbar_init(&sm.full[s], 1);
+            mbar_init(&sm.empty[s], kXrConsumers / 32);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const int n_chunks = (stride + kXrChunk - 1) / kXrChunk;
+
+    if (warp == kXrConsumers / 32) {
+        // ===================== producer warp: lane t streams tile t (A blocks 0..NQ-1, then the CTA's B blocks) =====================
+        const float *base = lane < NQ ? wa + (int64_t)lane * stride : wb + (int64_t)(lane - NQ) * stride;
+        const int o = (int)((reinterpret_cast<uintptr_t>(base) & 15u) >> 2);   // offset inside the 16-byte aligned superset
+        for (int c = 0; c < n_chunks; ++c) {
+            const int st = c % kXrStages;
+            if (c >= kXrStages) mbar_wait_warp(&sm.empty[st], (uint32_t)((c / kXrStages - 1) & 1), 20);
+            const int i0 = c * kXrChunk;
+            const int len = min(kXrChunk, stride - i0);
+            const uint32_t bytes = lane < n_tiles ? (uint32_t)((o + len + 3) & ~3) * 4u : 0u;
+            uint32_t total = bytes;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
+            if (lane == 0) mbar_arrive_expect_tx(&sm.full[st], total);
+            __syncwarp();
+            if (lane < n_tiles) bulk_g2s(&sm.tile[st][lane][0], base + i0 - o, bytes, &sm.full[st]);
+        }
+        return;
+    }
+
+    // ===================== consumer warps =====================
+    int off[NQ + kBlocksPerCta];
+#pragma unroll
+    for (int t = 0; t < NQ + kBlocksPerCta; ++t) {
+        const float *base = t < NQ ? wa + (int64_t)t * stride : wb + (int64_t)(t - NQ) * stride;
+        off[t] = (int)((reinterpret_cast<uintptr_t>(base) & 15u) >> 2);
+    }
+    double d[kBlocksPerCta][NQ], s2[kBlocksPerCta], sa = 0.0;
+#pragma unroll
+    for (int g = 0; g < kBlocksPerCta; ++g) {
+        s2[g] = 0.0;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) d[g][q] = 0.0;
+    }
+    for (int c = 0; c < n_chunks; ++c) {
+        const int st = c % kXrStages;
+        mbar_wait_warp(&sm.full[st], (uint32_t)(c / kXrStages) & 1u);
+        const int len = min(kXrChunk, stride - c * kXrChunk);
+        if (live == kBlocksPerCta) {
+#pragma unroll
+            for (int k = 0; k < kXrChunk / kXrConsumers; ++k) {
+                const int i = tid + k * kXrConsumers;
+                if (i < len) {
+                    double x[NQ], y[kBlocksPerCta];
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) x[q] = (double)sm.tile[st][q][off[q] + i];
+#pragma unroll
+                    for (int g = 0; g < kBlocksPerCta; ++g) y[g] = (double)sm.tile[st][NQ + g][off[NQ + g] + i];
+#pragma unroll
+                    for (int g = 0; g < kBlocksPerCta; ++g) {
+                        s2[g] = fma(y[g], y[g], s2[g]);
+#pragma unroll
+                        for (int q = 0; q < NQ; ++q) d[g][q] = fma(x[q], y[g], d[g][q]);
+                    }
+                    if (blockIdx.x == 0) {
+#pragma unroll
+                        for (int q = 0; q < NQ; ++q) sa = fma(x[q], x[q], sa);
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kXrChunk / kXrConsumers; ++k) {
+                const int i = tid + k * kXrConsumers;
+                if (i < len) {
+                    double x[NQ];
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) x[q] = (double)sm.tile[st][q][off[q] + i];
+#pragma unroll
+                    for (int g = 0; g < kBlocksPerCta; ++g) {
+                        if (g < live) {
+                            const double y = (double)sm.tile[st][NQ + g][off[NQ + g] + i];
+                            s2[g] = fma(y, y, s2[g]);
+#pragma unroll
+                            for (int q = 0; q < NQ; ++q) d[g][q] = fma(x[q], y, d[g][q]);
+                        }
+                    }
+                    if (blockIdx.x == 0) {
+#pragma unroll
+                        for (int q = 0; q < NQ; ++q) sa = fma(x[q], x[q], sa);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[st]);   // this warp is done reading the stage
+    }
+    double *pw = part + (size_t)w * (kMaxPieces + 1) * max_blocks;
+#pragma unroll
+    for (int g = 0; g < kBlocksPerCta; ++g) {
+        if (g < live) {  // CTA-uniform
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const double v = consumer_sum_256(d[g][q], sh);
+                if (tid == 0) pw[(size_t)q * max_blocks + m0 + g] = v;
+            }
+            const double v = consumer_sum_256(s2[g], sh);
+            if (tid == 0) pw[(size_t)kMaxPieces * max_blocks + m0 + g] = v;
+        }
+    }
+    if (blockIdx.x == 0) {
+        for (int i = NQ * stride + tid; i < win; i += kXrConsumers) {
+            const double x = (double)__ldg(wa + i);
+            sa = fma(x, x, sa);
+        }
+        sa = consumer_sum_256(sa, sh);
+        if (tid == 0) na2[w] = sa;
+    }
+}
+
 // one warp per window: candidate sums from the block partials (fixed order), then the same gates and scan as below
 __global__ void __launch_bounds__(32) xcorr_pick_blocks_kernel(const float *__restrict__ a, const float *__restrict__ b,
                                                                const int64_t *__restrict__ a_pos,
@@ -581,6 +763,14 @@ static bool xcorr_use_regs() {
     }();
     return v;
 }
+// NCFA_XCORR_IMPL=tma3: the 3-stage TMA form with a __syncthreads per chunk (before/after of the ring form)
+static bool xcorr_use_tma3() {
+    static const bool v = [] {
+        const char *e = getenv("NCFA_XCORR_IMPL");
+        return e && strcmp(e, "tma3") == 0;
+    }();
+    return v;
+}
 // NCFA_XCORR_IMPL=direct forces the one-CTA-per-candidate kernel (cross-check)
 static bool xcorr_force_direct() {
     static const bool v = [] {
@@ -631,6 +821,21 @@ extern "C" int ncfa_xcorr_search_batched(const float *d_a, const float *d_b, con
                     case 3: xcorr_blocks_kernel<3><<<g, kXcThreads, 0, st>>>(d_a, d_b, d_a_pos, d_b_lo, d_n_cand, max_blocks, win, stride, part, na2b); break;
                     default: xcorr_blocks_kernel<4><<<g, kXcThreads, 0, st>>>(d_a, d_b, d_a_pos, d_b_lo, d_n_cand, max_blocks, win, stride, part, na2b); break;
                 }
+            } else if (!xcorr_use_tma3()) {
+                int rc = 0;
+#define NCFA_XR_LAUNCH(NQ_)                                                                                             \
+    do {                                                                                                                \
+        if ((rc = ensure_dynamic_smem((const void *)xcorr_blocks_ring_kernel<NQ_>, sizeof(XrSmem<NQ_>)))) return rc;    \
+        xcorr_blocks_ring_kernel<NQ_><<<g, kXrThreads, sizeof(XrSmem<NQ_>), st>>>(d_a, d_b, d_a_pos, d_b_lo, d_n_cand,   \
+                                                                                  max_blocks, win, stride, part, na2b); \
+    } while (0)
+                switch (nq) {
+                    case 1: NCFA_XR_LAUNCH(1); break;
+                    case 2: NCFA_XR_LAUNCH(2); break;
+                    case 3: NCFA_XR_LAUNCH(3); break;
+                    default: NCFA_XR_LAUNCH(4); break;
+                }
+#undef NCFA_XR_LAUNCH
             } else {
                 int rc = 0;
 #define NCFA_XB_LAUNCH(NQ_)                                                                                             \

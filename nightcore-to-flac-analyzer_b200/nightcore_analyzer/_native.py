@@ -37,6 +37,7 @@ _SIGNATURES = {
     "ncfa_param_upload": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "ncfa_profile_enable": (None, [c_int]),
     "ncfa_profile_report": (c_int, [ctypes.c_char_p, c_size_t]),
+    "ncfa_profile_timeline": (c_int, [ctypes.c_char_p, c_size_t]),
     "ncfa_window_energy": (c_int, [_P, _P, _P, c_int, _P, _P]),
     "ncfa_rms_frames": (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
     "ncfa_trim_workspace_bytes": (c_size_t, [c_int, c_int]),
@@ -105,6 +106,17 @@ def profile_report() -> dict:
     for line in buf.value.decode().splitlines():
         name, n, ms = line.split(",")
         out[name] = (int(n), float(ms))
+    return out
+
+
+def profile_timeline() -> list:
+    """[(kernel name, stream, t0_ms, t1_ms)] of every launch since profiling was enabled; clears the records."""
+    buf = ctypes.create_string_buffer(1 << 22)
+    check(lib.ncfa_profile_timeline(buf, len(buf)), "ncfa_profile_timeline")
+    out = []
+    for line in buf.value.decode().splitlines():
+        name, st, t0, t1 = line.split(",")
+        out.append((name, st, float(t0), float(t1)))
     return out
 
 
