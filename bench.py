@@ -238,7 +238,7 @@ def run_gpu(args):
     pinned = nbatch.pin_pairs(pairs_np, SR)
     n_mine = len(my_ids)
     sub = max(1, min(args.sub_batch, max(16, -(-n_mine // 4)))) if n_mine else 1     # at least ~4 sub-batches per rank
-    sizes = [min(sub, n_mine - s) for s in range(0, n_mine, sub)]
+    sizes = nbatch.stagger_sizes(n_mine, sub, args.workers)          # first job short: the workers run out of phase
     starts = [sum(sizes[:j]) for j in range(len(sizes))]
     resident = [nbatch.upload(pinned, k, start_pair=s) for s, k in zip(starts, sizes)]
     torch.cuda.synchronize()

@@ -349,36 +349,33 @@ __global__ void __launch_bounds__(kXcThreads) xcorr_blocks_tma_kernel(const floa
 // (2 KB copies, six stages, two CTAs per SM) ran at 1.5 TB/s against 2.6 TB/s for the 4 KB copies above: the SM's copy
 // engine spends a fixed ~200 cycles per bulk copy at these 16-byte-aligned addresses, so bytes per copy set the rate —
 // hence 2048-sample chunks (8 KB copies), three stages (197 KB), one CTA of 16 consumer warps per SM.
-constexpr int kXrChunk = 2048;
-constexpr int kXrStages = 3;
-constexpr int kXrTileFloats = kXrChunk + 8;
-constexpr int kXrConsumers = 512;                   // 16 consumer warps
-constexpr int kXrThreads = kXrConsumers + 32;       // + the producer warp
-
-template <int NQ>
+// G = B blocks per CTA.  The A blocks are re-read by every CTA of a window, so the bytes a CTA pulls through the copy
+// engine are (NQ + G) / G times its algorithmic share: 2x at G = 4, 1.5x at G = 8 (40 float64 accumulators per thread).
+template <int NQ, int G, int CHUNK, int STAGES, int CONSUMERS>
 struct XrSmem {
-    float tile[kXrStages][NQ + kBlocksPerCta][kXrTileFloats];
-    uint64_t full[kXrStages], empty[kXrStages];
+    float tile[STAGES][NQ + G][CHUNK + 8];
+    uint64_t full[STAGES], empty[STAGES];
 };
 
 // block sum over the consumer threads (named barrier 1: the producer warp is not part of it)
-__device__ __forceinline__ double consumer_sum_256(double v, double *sh) {
+template <int CONSUMERS>
+__device__ __forceinline__ double consumer_sum(double v, double *sh) {
     v = warp_sum(v);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
-    asm volatile("bar.sync 1, %0;" ::"n"(kXrConsumers) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");
     double s = 0.0;
     if (threadIdx.x == 0) {
-        for (int w = 0; w < kXrConsumers / 32; ++w) s += sh[w];
+        for (int w = 0; w < CONSUMERS / 32; ++w) s += sh[w];
         sh[0] = s;
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(kXrConsumers) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");
     s = sh[0];
-    asm volatile("bar.sync 1, %0;" ::"n"(kXrConsumers) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");
     return s;
 }
 
-template <int NQ>
-__global__ void __launch_bounds__(kXrThreads, 1) xcorr_blocks_ring_kernel(const float *__restrict__ a,
+template <int NQ, int G, int CHUNK, int STAGES, int CONSUMERS>
+__global__ void __launch_bounds__(CONSUMERS + 32, 1) xcorr_blocks_ring_kernel(const float *__restrict__ a,
                                                                        const float *__restrict__ b,
                                                                        const int64_t *__restrict__ a_pos,
                                                                        const int64_t *__restrict__ b_lo,
@@ -387,39 +384,39 @@ __global__ void __launch_bounds__(kXrThreads, 1) xcorr_blocks_ring_kernel(const 
                                                                        double *__restrict__ na2) {
     using namespace tc05;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    XrSmem<NQ> &sm = *reinterpret_cast<XrSmem<NQ> *>(smem_raw);
-    __shared__ double sh[kXrConsumers / 32];
+    XrSmem<NQ, G, CHUNK, STAGES, CONSUMERS> &sm = *reinterpret_cast<XrSmem<NQ, G, CHUNK, STAGES, CONSUMERS> *>(smem_raw);
+    __shared__ double sh[CONSUMERS / 32];
     const int w = blockIdx.y;
     const int nc = n_cand[w];
     if (nc <= 0 && blockIdx.x != 0) return;
     const int n_blocks = nc > 0 ? nc + NQ - 1 : 0;
-    const int m0 = blockIdx.x * kBlocksPerCta;
+    const int m0 = blockIdx.x * G;
     if (m0 >= n_blocks && blockIdx.x != 0) return;
     const float *wa = a + a_pos[w];
     const float *wb = b + b_lo[w] + (int64_t)m0 * stride;
-    const int live = max(0, min(kBlocksPerCta, n_blocks - m0));
+    const int live = max(0, min(G, n_blocks - m0));
     const int n_tiles = NQ + live;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < kXrStages; ++s) {
+        for (int s = 0; s < STAGES; ++s) {
             mbar_init(&sm.full[s], 1);
-            mbar_init(&sm.empty[s], kXrConsumers / 32);
+            mbar_init(&sm.empty[s], CONSUMERS / 32);
         }
         fence_mbar_init();
     }
     __syncthreads();
-    const int n_chunks = (stride + kXrChunk - 1) / kXrChunk;
+    const int n_chunks = (stride + CHUNK - 1) / CHUNK;
 
-    if (warp == kXrConsumers / 32) {
+    if (warp == CONSUMERS / 32) {
         // ===================== producer warp: lane t streams tile t (A blocks 0..NQ-1, then the CTA's B blocks) =====================
         const float *base = lane < NQ ? wa + (int64_t)lane * stride : wb + (int64_t)(lane - NQ) * stride;
         const int o = (int)((reinterpret_cast<uintptr_t>(base) & 15u) >> 2);   // offset inside the 16-byte aligned superset
         for (int c = 0; c < n_chunks; ++c) {
-            const int st = c % kXrStages;
-            if (c >= kXrStages) mbar_wait_warp(&sm.empty[st], (uint32_t)((c / kXrStages - 1) & 1), 20);
-            const int i0 = c * kXrChunk;
-            const int len = min(kXrChunk, stride - i0);
+            const int st = c % STAGES;
+            if (c >= STAGES) mbar_wait_warp(&sm.empty[st], (uint32_t)((c / STAGES - 1) & 1), 20);
+            const int i0 = c * CHUNK;
+            const int len = min(CHUNK, stride - i0);
             const uint32_t bytes = lane < n_tiles ? (uint32_t)((o + len + 3) & ~3) * 4u : 0u;
             uint32_t total = bytes;
 #pragma unroll
@@ -432,35 +429,35 @@ __global__ void __launch_bounds__(kXrThreads, 1) xcorr_blocks_ring_kernel(const 
     }
 
     // ===================== consumer warps =====================
-    int off[NQ + kBlocksPerCta];
+    int off[NQ + G];
 #pragma unroll
-    for (int t = 0; t < NQ + kBlocksPerCta; ++t) {
+    for (int t = 0; t < NQ + G; ++t) {
         const float *base = t < NQ ? wa + (int64_t)t * stride : wb + (int64_t)(t - NQ) * stride;
         off[t] = (int)((reinterpret_cast<uintptr_t>(base) & 15u) >> 2);
     }
-    double d[kBlocksPerCta][NQ], s2[kBlocksPerCta], sa = 0.0;
+    double d[G][NQ], s2[G], sa = 0.0;
 #pragma unroll
-    for (int g = 0; g < kBlocksPerCta; ++g) {
+    for (int g = 0; g < G; ++g) {
         s2[g] = 0.0;
 #pragma unroll
         for (int q = 0; q < NQ; ++q) d[g][q] = 0.0;
     }
     for (int c = 0; c < n_chunks; ++c) {
-        const int st = c % kXrStages;
-        mbar_wait_warp(&sm.full[st], (uint32_t)(c / kXrStages) & 1u);
-        const int len = min(kXrChunk, stride - c * kXrChunk);
-        if (live == kBlocksPerCta) {
+        const int st = c % STAGES;
+        mbar_wait_warp(&sm.full[st], (uint32_t)(c / STAGES) & 1u);
+        const int len = min(CHUNK, stride - c * CHUNK);
+        if (live == G) {
 #pragma unroll
-            for (int k = 0; k < kXrChunk / kXrConsumers; ++k) {
-                const int i = tid + k * kXrConsumers;
+            for (int k = 0; k < CHUNK / CONSUMERS; ++k) {
+                const int i = tid + k * CONSUMERS;
                 if (i < len) {
-                    double x[NQ], y[kBlocksPerCta];
+                    double x[NQ], y[G];
 #pragma unroll
                     for (int q = 0; q < NQ; ++q) x[q] = (double)sm.tile[st][q][off[q] + i];
 #pragma unroll
-                    for (int g = 0; g < kBlocksPerCta; ++g) y[g] = (double)sm.tile[st][NQ + g][off[NQ + g] + i];
+                    for (int g = 0; g < G; ++g) y[g] = (double)sm.tile[st][NQ + g][off[NQ + g] + i];
 #pragma unroll
-                    for (int g = 0; g < kBlocksPerCta; ++g) {
+                    for (int g = 0; g < G; ++g) {
                         s2[g] = fma(y[g], y[g], s2[g]);
 #pragma unroll
                         for (int q = 0; q < NQ; ++q) d[g][q] = fma(x[q], y[g], d[g][q]);
@@ -473,14 +470,14 @@ __global__ void __launch_bounds__(kXrThreads, 1) xcorr_blocks_ring_kernel(const 
             }
         } else {
 #pragma unroll
-            for (int k = 0; k < kXrChunk / kXrConsumers; ++k) {
-                const int i = tid + k * kXrConsumers;
+            for (int k = 0; k < CHUNK / CONSUMERS; ++k) {
+                const int i = tid + k * CONSUMERS;
                 if (i < len) {
                     double x[NQ];
 #pragma unroll
                     for (int q = 0; q < NQ; ++q) x[q] = (double)sm.tile[st][q][off[q] + i];
 #pragma unroll
-                    for (int g = 0; g < kBlocksPerCta; ++g) {
+                    for (int g = 0; g < G; ++g) {
                         if (g < live) {
                             const double y = (double)sm.tile[st][NQ + g][off[NQ + g] + i];
                             s2[g] = fma(y, y, s2[g]);
@@ -500,23 +497,173 @@ __global__ void __launch_bounds__(kXrThreads, 1) xcorr_blocks_ring_kernel(const 
     }
     double *pw = part + (size_t)w * (kMaxPieces + 1) * max_blocks;
 #pragma unroll
-    for (int g = 0; g < kBlocksPerCta; ++g) {
+    for (int g = 0; g < G; ++g) {
         if (g < live) {  // CTA-uniform
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
-                const double v = consumer_sum_256(d[g][q], sh);
+                const double v = consumer_sum<CONSUMERS>(d[g][q], sh);
                 if (tid == 0) pw[(size_t)q * max_blocks + m0 + g] = v;
             }
-            const double v = consumer_sum_256(s2[g], sh);
+            const double v = consumer_sum<CONSUMERS>(s2[g], sh);
             if (tid == 0) pw[(size_t)kMaxPieces * max_blocks + m0 + g] = v;
         }
     }
     if (blockIdx.x == 0) {
-        for (int i = NQ * stride + tid; i < win; i += kXrConsumers) {
+        for (int i = NQ * stride + tid; i < win; i += CONSUMERS) {
             const double x = (double)__ldg(wa + i);
             sa = fma(x, x, sa);
         }
-        sa = consumer_sum_256(sa, sh);
+        sa = consumer_sum<CONSUMERS>(sa, sh);
+        if (tid == 0) na2[w] = sa;
+    }
+}
+
+// ---- ring form with the A blocks in registers (the default) ------------------------------------------------------------
+// ncu on the ring kernel above (profiles/r2i: 4 or 8 B blocks per CTA, 2 KB / 4 KB / 8 KB copies, 3-6 stages, one or two
+// CTAs per SM) always lands on the same ~18 B/clk of bulk-copy traffic per SM with the consumers waiting on the full
+// barriers, i.e. the copy engine of an SM sustains only so many bytes in flight; what counts is how many of those bytes
+// are algorithmic.  The A blocks of a window are re-read by each of its CTAs and are L1/L2 resident, so here they do not
+// go through the copy engine at all: a consumer thread loads the A samples of its own indices straight into registers
+// (coalesced 4-byte loads, issued one chunk ahead), and the ring carries only the CTA's eight B blocks — every byte the
+// copy engine moves is read from HBM exactly once.
+template <int G, int CHUNK, int STAGES>
+struct XaSmem {
+    float tile[STAGES][G][CHUNK + 8];
+    uint64_t full[STAGES], empty[STAGES];
+};
+
+template <int NQ, int G, int CHUNK, int STAGES, int CONSUMERS>
+__global__ void __launch_bounds__(CONSUMERS + 32, 1) xcorr_blocks_areg_kernel(const float *__restrict__ a,
+                                                                              const float *__restrict__ b,
+                                                                              const int64_t *__restrict__ a_pos,
+                                                                              const int64_t *__restrict__ b_lo,
+                                                                              const int32_t *__restrict__ n_cand,
+                                                                              int max_blocks, int win, int stride,
+                                                                              double *__restrict__ part,
+                                                                              double *__restrict__ na2) {
+    using namespace tc05;
+    constexpr int KPER = CHUNK / CONSUMERS;  // sample indices per thread per chunk
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    XaSmem<G, CHUNK, STAGES> &sm = *reinterpret_cast<XaSmem<G, CHUNK, STAGES> *>(smem_raw);
+    __shared__ double sh[CONSUMERS / 32];
+    const int w = blockIdx.y;
+    const int nc = n_cand[w];
+    if (nc <= 0 && blockIdx.x != 0) return;
+    const int n_blocks = nc > 0 ? nc + NQ - 1 : 0;
+    const int m0 = blockIdx.x * G;
+    if (m0 >= n_blocks && blockIdx.x != 0) return;
+    const float *wa = a + a_pos[w];
+    const float *wb = b + b_lo[w] + (int64_t)m0 * stride;
+    const int live = max(0, min(G, n_blocks - m0));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&sm.full[s], 1);
+            mbar_init(&sm.empty[s], CONSUMERS / 32);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const int n_chunks = live > 0 ? (stride + CHUNK - 1) / CHUNK : 0;
+
+    if (warp == CONSUMERS / 32) {
+        // ===================== producer warp: lane g streams B block m0 + g =====================
+        const float *base = wb + (int64_t)lane * stride;
+        const int o = (int)((reinterpret_cast<uintptr_t>(base) & 15u) >> 2);   // offset inside the 16-byte aligned superset
+        for (int c = 0; c < n_chunks; ++c) {
+            const int st = c % STAGES;
+            if (c >= STAGES) mbar_wait_warp(&sm.empty[st], (uint32_t)((c / STAGES - 1) & 1), 20);
+            const int i0 = c * CHUNK;
+            const int len = min(CHUNK, stride - i0);
+            const uint32_t bytes = lane < live ? (uint32_t)((o + len + 3) & ~3) * 4u : 0u;
+            uint32_t total = bytes;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
+            if (lane == 0) mbar_arrive_expect_tx(&sm.full[st], total);
+            __syncwarp();
+            if (lane < live) bulk_g2s(&sm.tile[st][lane][0], base + i0 - o, bytes, &sm.full[st]);
+        }
+        return;
+    }
+
+    // ===================== consumer warps =====================
+    int off[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) off[g] = (int)((reinterpret_cast<uintptr_t>(wb + (int64_t)g * stride) & 15u) >> 2);
+    double d[G][NQ], s2[G], sa = 0.0;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        s2[g] = 0.0;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) d[g][q] = 0.0;
+    }
+    float xn[KPER][NQ];  // A samples of the NEXT chunk (0 beyond the block's end: they then add nothing)
+    auto load_a = [&](int c) {
+#pragma unroll
+        for (int k = 0; k < KPER; ++k) {
+            const int i = c * CHUNK + tid + k * CONSUMERS;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) xn[k][q] = (c < n_chunks && i < stride) ? __ldg(wa + (int64_t)q * stride + i) : 0.0f;
+        }
+    };
+    load_a(0);
+    for (int c = 0; c < n_chunks; ++c) {
+        const int st = c % STAGES;
+        float xc[KPER][NQ];
+#pragma unroll
+        for (int k = 0; k < KPER; ++k)
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) xc[k][q] = xn[k][q];
+        load_a(c + 1);  // in flight while this chunk is consumed
+        mbar_wait_warp(&sm.full[st], (uint32_t)(c / STAGES) & 1u);
+        const int len = min(CHUNK, stride - c * CHUNK);
+#pragma unroll
+        for (int k = 0; k < KPER; ++k) {
+            const int i = tid + k * CONSUMERS;
+            if (i < len) {
+                double x[NQ];
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) x[q] = (double)xc[k][q];
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    if (g < live) {  // CTA-uniform
+                        const double y = (double)sm.tile[st][g][off[g] + i];
+                        s2[g] = fma(y, y, s2[g]);
+#pragma unroll
+                        for (int q = 0; q < NQ; ++q) d[g][q] = fma(x[q], y, d[g][q]);
+                    }
+                }
+                if (blockIdx.x == 0) {
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) sa = fma(x[q], x[q], sa);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[st]);   // this warp is done reading the stage
+    }
+    double *pw = part + (size_t)w * (kMaxPieces + 1) * max_blocks;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        if (g < live) {  // CTA-uniform
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const double v = consumer_sum<CONSUMERS>(d[g][q], sh);
+                if (tid == 0) pw[(size_t)q * max_blocks + m0 + g] = v;
+            }
+            const double v = consumer_sum<CONSUMERS>(s2[g], sh);
+            if (tid == 0) pw[(size_t)kMaxPieces * max_blocks + m0 + g] = v;
+        }
+    }
+    if (blockIdx.x == 0) {
+        // ‖wa‖²: the block part was accumulated above when the CTA had B blocks; otherwise (no candidate) sum it here
+        const int from = live > 0 ? NQ * stride : 0;
+        for (int i = from + tid; i < win; i += CONSUMERS) {
+            const double x = (double)__ldg(wa + i);
+            sa = fma(x, x, sa);
+        }
+        sa = consumer_sum<CONSUMERS>(sa, sh);
         if (tid == 0) na2[w] = sa;
     }
 }
@@ -771,6 +918,22 @@ static bool xcorr_use_tma3() {
     }();
     return v;
 }
+// NCFA_XCORR_IMPL=ring4: the ring form with four B blocks per CTA (before/after of the eight-block default)
+static bool xcorr_g4() {
+    static const bool v = [] {
+        const char *e = getenv("NCFA_XCORR_IMPL");
+        return e && strcmp(e, "ring4") == 0;
+    }();
+    return v;
+}
+// NCFA_XCORR_IMPL=ring8: eight B blocks per CTA with the A blocks in the ring too (before/after of the register-A default)
+static bool xcorr_ring8() {
+    static const bool v = [] {
+        const char *e = getenv("NCFA_XCORR_IMPL");
+        return e && strcmp(e, "ring8") == 0;
+    }();
+    return v;
+}
 // NCFA_XCORR_IMPL=direct forces the one-CTA-per-candidate kernel (cross-check)
 static bool xcorr_force_direct() {
     static const bool v = [] {
@@ -825,9 +988,27 @@ extern "C" int ncfa_xcorr_search_batched(const float *d_a, const float *d_b, con
                 int rc = 0;
 #define NCFA_XR_LAUNCH(NQ_)                                                                                             \
     do {                                                                                                                \
-        if ((rc = ensure_dynamic_smem((const void *)xcorr_blocks_ring_kernel<NQ_>, sizeof(XrSmem<NQ_>)))) return rc;    \
-        xcorr_blocks_ring_kernel<NQ_><<<g, kXrThreads, sizeof(XrSmem<NQ_>), st>>>(d_a, d_b, d_a_pos, d_b_lo, d_n_cand,   \
-                                                                                  max_blocks, win, stride, part, na2b); \
+        if (!xcorr_g4() && !xcorr_ring8()) {                                                                            \
+            using Sm = XaSmem<8, 1024, 6>;                                                                              \
+            auto kfn = xcorr_blocks_areg_kernel<NQ_, 8, 1024, 6, 256>;                                                  \
+            if ((rc = ensure_dynamic_smem((const void *)kfn, sizeof(Sm)))) return rc;                                   \
+            dim3 g8((max_cand + nq - 1 + 7) / 8, n_windows);                                                            \
+            kfn<<<g8, 256 + 32, sizeof(Sm), st>>>(d_a, d_b, d_a_pos, d_b_lo, d_n_cand, max_blocks, win, stride, part,   \
+                                                  na2b);                                                                \
+        } else if (xcorr_g4()) {                                                                                        \
+            using Sm = XrSmem<NQ_, 4, 2048, 3, 512>;                                                                    \
+            auto kfn = xcorr_blocks_ring_kernel<NQ_, 4, 2048, 3, 512>;                                                  \
+            if ((rc = ensure_dynamic_smem((const void *)kfn, sizeof(Sm)))) return rc;                                   \
+            kfn<<<g, 512 + 32, sizeof(Sm), st>>>(d_a, d_b, d_a_pos, d_b_lo, d_n_cand, max_blocks, win, stride, part,    \
+                                                 na2b);                                                                 \
+        } else {                                                                                                        \
+            using Sm = XrSmem<NQ_, 8, 1024, 4, 256>;                                                                    \
+            auto kfn = xcorr_blocks_ring_kernel<NQ_, 8, 1024, 4, 256>;                                                  \
+            if ((rc = ensure_dynamic_smem((const void *)kfn, sizeof(Sm)))) return rc;                                   \
+            dim3 g8((max_cand + nq - 1 + 7) / 8, n_windows);                                                            \
+            kfn<<<g8, 256 + 32, sizeof(Sm), st>>>(d_a, d_b, d_a_pos, d_b_lo, d_n_cand, max_blocks, win, stride, part,   \
+                                                  na2b);                                                                \
+        }                                                                                                               \
     } while (0)
                 switch (nq) {
                     case 1: NCFA_XR_LAUNCH(1); break;

@@ -18,3 +18,21 @@ def test_plan_grows_geometrically_then_splits_evenly():
     assert all(b <= 2 * a for a, b in zip(sizes, sizes[1:]))       # an upload never outgrows the compute before it
     tail = sizes[len(head) + 1:]
     assert max(tail) - min(tail) <= 1                              # no short tail job
+
+
+@pytest.mark.parametrize("n,sub,workers", [(1000, 125, 2), (125, 32, 2), (500, 125, 3), (90, 125, 2), (1, 1, 2), (0, 16, 2), (1000, 125, 1)])
+def test_staggered_resident_plan(n, sub, workers):
+    sizes = batch.stagger_sizes(n, sub, workers)
+    assert sum(sizes) == n
+    assert all(0 < s <= sub for s in sizes)
+    if workers >= 2 and n > sub:
+        assert sizes[0] == max(1, sub // workers)                  # the first job is short: workers run out of phase
+        assert max(sizes[1:]) - min(sizes[1:]) <= 1
+
+
+def test_gil_handoff_is_restored():
+    import sys
+    before = sys.getswitchinterval()
+    with batch._fast_gil_handoff():
+        assert sys.getswitchinterval() <= 2e-4
+    assert sys.getswitchinterval() == before
