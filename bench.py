@@ -243,7 +243,6 @@ def run_gpu(args):
     resident = [nbatch.upload(pinned, k, start_pair=s) for s, k in zip(starts, sizes)]
     torch.cuda.synchronize()
     resident_bytes = sum(st.h2d_bytes for st in resident)
-    sizes_e2e = nbatch.plan_subbatches(n_mine, sub, args.workers, first=max(8, min(sub, n_mine // 12)))
 
     def barrier():
         if world > 1:
@@ -343,7 +342,7 @@ def run_gpu(args):
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": f"synthetic ({n_distinct} distinct pairs tiled to {total_pairs}; oracle/synth.py)",
             "config": workload_config(total_pairs, args.pair_sec),
-            "schedule": {"sub_batch_pairs": sub, "resident_sub_batches": sizes, "e2e_sub_batches": sizes_e2e,
+            "schedule": {"sub_batch_pairs": sub, "resident_sub_batches": sizes, "e2e_sub_batches": stats_e.get("sub_batches"),
                          "host_workers": args.workers, "windows_per_step": windows, "pairs_ok": n_ok,
                          "pitch": not args.no_pitch, "ibi": not args.no_ibi,
                          "resident_audio_mb_per_rank": round(resident_bytes / 1e6, 1)},

@@ -774,15 +774,30 @@ constexpr int kTcTmemCols = 512;                         // 320 (A ring) + 2 × 
 constexpr int kTcAPre = 4;                               // k-tiles of A rows in flight (cp.async ring in shared memory)
 constexpr int kTcAPlane = kTcFrames + 1;                 // float4 per chunk plane of the A staging ring
 
-struct TcSmem {
-    alignas(1024) unsigned char b[kTcBStages][kTcBStageBytes];
-    float4 arow[kTcAPre][8 * kTcAPlane];  // [slot][16-byte chunk · kTcAPlane + frame]: the odd plane stride keeps both the
+template <int BST, int PRE = kTcAPre>
+struct TcSmemT {
+    alignas(1024) unsigned char b[BST][kTcBStageBytes];
+    float4 arow[PRE][8 * kTcAPlane];  // [slot][16-byte chunk · kTcAPlane + frame]: the odd plane stride keeps both the
                                           // (8 rows × 4 chunks) cp.async writes and the per-row LDS.128 reads conflict free
     float chroma_part[kTcFrames][16];    // [frame][4·q + j]: partial chroma (3q + j) mod 12 of column quarter q
     alignas(8) uint64_t full_a[kTcAStages], empty_a[kTcAStages], full_b[kTcBStages], empty_b[kTcBStages];
     uint64_t acc_full[2], acc_empty[2];
     uint32_t tmem_base;
     double red[4][kChroma];
+};
+using TcSmem = TcSmemT<kTcBStages>;
+
+// Pipeline shape of the octave-major kernel.  One: a deep pipeline that owns the SM (5 A stages in TMEM, 5 B images in
+// shared memory, two accumulators, all 512 TMEM columns).  Two: TWO CTAs per SM, each with a shallow pipeline (2 A stages,
+// 2 B images, one accumulator, 256 TMEM columns, 107 KB of shared memory).  The timing experiments (NCFA_TC_DEBUG,
+// profiles/r2l_cqt_debug.log) show that with A traffic, B traffic AND the MMAs all switched off the kernel still takes
+// 12.3 of its 13.4 ms: what paces it is the latency of one CTA's serial producer → MMA → release chain, with two or three
+// warps per scheduler to hide it.  A second resident CTA overlaps two such chains on the same tensor pipe.
+struct TcOne {
+    static constexpr int kA = kTcAStages, kB = kTcBStages, kAcc = 2, kTmem = 512, kMinBlocks = 1, kPre = kTcAPre;
+};
+struct TcTwo {
+    static constexpr int kA = 2, kB = 2, kAcc = 1, kTmem = 256, kMinBlocks = 2, kPre = 3;   // 100 KB of shared memory per CTA
 };
 
 __device__ __forceinline__ void tc_load_row8(const float *__restrict__ y, int64_t pos, int len, float (&x)[8]) {
@@ -826,8 +841,8 @@ __device__ __forceinline__ void tc_epilogue_quarter(uint32_t acc_addr, float (&p
 }
 
 // DBG = false is the production instantiation (the timing-experiment switches compile away); DBG = true honours `dbg`.
-template <bool DBG>
-__global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__restrict__ audio,
+template <bool DBG, typename CFG>
+__global__ void __launch_bounds__(kTcThreads, CFG::kMinBlocks) cqt_tc_kernel(const float *__restrict__ audio,
                                                                const int64_t *__restrict__ seg_off,
                                                                const int32_t *__restrict__ seg_len,
                                                                const float *__restrict__ pyr, PyrOffsets po,
@@ -837,7 +852,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
     using namespace tc05;
     const int dbg = DBG ? dbg_arg : 0;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    TcSmem &sm = *reinterpret_cast<TcSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    using Smem = TcSmemT<CFG::kB, CFG::kPre>;
+    constexpr int kPre = CFG::kPre;
+    Smem &sm = *reinterpret_cast<Smem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int kAS = CFG::kA, kBS = CFG::kB;           // A stages (TMEM), B stages (shared memory); equal: one release barrier
+    static_assert(kAS == kBS, "A and B stages share the release barrier");
+    constexpr int kAccCol0 = kAS * kTcACols;
+    static_assert(kAccCol0 + CFG::kAcc * kTcAccN <= CFG::kTmem, "TMEM budget");
     const int seg = blockIdx.y;
     const int n = seg_len[seg];
     const int n_frames = cqt_frames(n);
@@ -846,11 +867,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        for (int i = 0; i < kTcAStages; ++i) {
+        for (int i = 0; i < kAS; ++i) {
             mbar_init(&sm.full_a[i], kTcFrameWarps);  // one arrival per frame warp
             mbar_init(&sm.empty_a[i], 1);
         }
-        for (int i = 0; i < kTcBStages; ++i) {
+        for (int i = 0; i < kBS; ++i) {
             mbar_init(&sm.full_b[i], 1);
             mbar_init(&sm.empty_b[i], 1);
         }
@@ -860,7 +881,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
         }
         fence_mbar_init();
     }
-    if (warp == kTcFrameWarps) tmem_alloc(&sm.tmem_base, kTcTmemCols);
+    if (warp == kTcFrameWarps) tmem_alloc(&sm.tmem_base, CFG::kTmem);
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
@@ -888,10 +909,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
             for (int j = 0; j < 4; ++j) part[a][j] = 0.0f;
 
         auto epilogue = [&](int o) {
-            const int buf = o & 1;
-            mbar_wait_warp(&sm.acc_full[buf], (uint32_t)((o >> 1) & 1), 100);
+            const int buf = CFG::kAcc == 2 ? (o & 1) : 0;
+            mbar_wait_warp(&sm.acc_full[buf], (uint32_t)(CFG::kAcc == 2 ? (o >> 1) & 1 : o & 1), 100);
             fence_after_sync();
-            const uint32_t acc = tmem + lane_base + (uint32_t)(kTcAccCol0 + buf * kTcAccN);
+            const uint32_t acc = tmem + lane_base + (uint32_t)(kAccCol0 + buf * kTcAccN);
 #pragma unroll
             for (int a = 0; a < kQPer; ++a) {
                 switch (q * kQPer + a) {  // warp-uniform
@@ -906,7 +927,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
             if (lane == 0) mbar_arrive(&sm.acc_empty[buf]);
         };
 
-        // A rows stream through a cp.async ring (kTcAPre k-tiles ahead, flat over octaves × k-tiles): thread (f, q) owns
+        // A rows stream through a cp.async ring (kPre k-tiles ahead, flat over octaves × k-tiles): thread (f, q) owns
         // kTcVals consecutive samples (kTcVals/4 16-byte chunks) of row f in every k-tile.  Zero padding outside [0, len)
         // comes from the src-size (zfill) form — row starts are multiples of 4 samples, so a chunk never straddles 0.
         // The per-tile address arithmetic is kept to a handful of 32-bit operations: this instruction stream, not the
@@ -947,7 +968,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
                 oct_fast = oct_async && __all_sync(0xffffffffu, inside);
                 ybase = ylev + row0;
             }
-            const uint32_t slot_u32 = arow_u32 + (uint32_t)(it % kTcAPre) * kSlotBytes + slot_off;
+            const uint32_t slot_u32 = arow_u32 + (uint32_t)(it % kPre) * kSlotBytes + slot_off;
             if (DBG && (dbg & 2)) {  // timing experiment: no A traffic
             } else if (oct_fast) {
                 const float *src = ybase + kt * kTcKT;
@@ -985,21 +1006,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        for (int it = 0; it < kTcAPre - 1; ++it) issue(it);
+        for (int it = 0; it < kPre - 1; ++it) issue(it);
         bool pending = false;
         for (int it = 0; it < kIters; ++it) {
-            if (it + kTcAPre - 1 < kIters) issue(it + kTcAPre - 1);
+            if (it + kPre - 1 < kIters) issue(it + kPre - 1);
             else asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group %0;" ::"n"(kTcAPre - 1) : "memory");
+            asm volatile("cp.async.wait_group %0;" ::"n"(kPre - 1) : "memory");
             __syncwarp();  // the row this thread reads was fetched by other lanes of its warp
             const int o = it >> 5, kt = it & 31;
-            const int st = it % kTcAStages;
+            const int st = it % kAS;
             uint32_t h[kTcVals], l[kTcVals];
             {
                 // x = hi + lo with hi = x truncated to tf32 (one LOP3; cvt.rna.tf32 is a five-instruction sequence here) and
                 // lo = x − hi exactly; |lo| < 2^-10·|x|, and the tensor core reads lo's leading 11 bits: the split is good to
                 // 2^-20·|x|, on a 1e-4 tolerance (measured worst chroma error 5e-7 of the maximum, tests/test_gpu_pitch.py)
-                const uint32_t rd = arow_u32 + (uint32_t)(it % kTcAPre) * kSlotBytes +
+                const uint32_t rd = arow_u32 + (uint32_t)(it % kPre) * kSlotBytes +
                                     (uint32_t)(((kChunks * q) * kTcAPlane + f) * sizeof(float4));
 #pragma unroll
                 for (int c = 0; c < kChunks; ++c) {
@@ -1021,9 +1042,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
                 if (!(DBG && (dbg & 8))) wait_st();
                 fence_before_sync();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.full_a[(it - 1) % kTcAStages]);
+                if (lane == 0) mbar_arrive(&sm.full_a[(it - 1) % kAS]);
             }
-            mbar_wait_warp(&sm.empty_a[st], (uint32_t)(((it / kTcAStages) & 1) ^ 1), 40);
+            mbar_wait_warp(&sm.empty_a[st], (uint32_t)(((it / kAS) & 1) ^ 1), 40);
             fence_after_sync();
             const uint32_t a0 = tmem + lane_base + (uint32_t)(st * kTcACols + kTcVals * q);
             tmem_st_vals(a0, h);
@@ -1035,10 +1056,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.full_a[st]);
                 pending = false;
-                if (o > 0) epilogue(o - 1);
+                // two accumulators: octave o−1 is read while the MMAs of octave o+1 run; one accumulator: the MMAs of
+                // the next octave wait for this read, so it has to happen right here
+                if (CFG::kAcc == 2) {
+                    if (o > 0) epilogue(o - 1);
+                } else {
+                    epilogue(o);
+                }
             }
         }
-        epilogue(kOctaves - 1);
+        if (CFG::kAcc == 2) epilogue(kOctaves - 1);
 
         // ---- combine the four column quarters of every frame, librosa.util.normalize(norm=inf) per frame, then the
         // tile's sum over frames (float64)
@@ -1076,15 +1103,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
         // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
         constexpr uint32_t idesc = idesc_tf32(kTcFrames, kTcN);  // M 128 × N 80 × K 8
         for (int o = 0; o < kOctaves; ++o) {
-            const int buf = o & 1;
-            mbar_wait_warp(&sm.acc_empty[buf], (uint32_t)(((o >> 1) & 1) ^ 1));
+            const int buf = CFG::kAcc == 2 ? (o & 1) : 0;
+            mbar_wait_warp(&sm.acc_empty[buf], (uint32_t)((CFG::kAcc == 2 ? (o >> 1) & 1 : o & 1) ^ 1));
             fence_after_sync();
-            const uint32_t d = tmem + (uint32_t)(kTcAccCol0 + buf * kTcAccN);
+            const uint32_t d = tmem + (uint32_t)(kAccCol0 + buf * kTcAccN);
             for (int kt = 0; kt < kKTiles; ++kt) {
                 const int it = o * kKTiles + kt;
-                const int sa = it % kTcAStages, sb = it % kTcBStages;
-                mbar_wait_warp(&sm.full_a[sa], (uint32_t)((it / kTcAStages) & 1));
-                mbar_wait_warp(&sm.full_b[sb], (uint32_t)((it / kTcBStages) & 1));
+                const int sa = it % kAS, sb = it % kBS;
+                mbar_wait_warp(&sm.full_a[sa], (uint32_t)((it / kAS) & 1));
+                mbar_wait_warp(&sm.full_b[sb], (uint32_t)((it / kBS) & 1));
                 fence_after_sync();
                 const uint64_t bh = smem_desc_k128(sm.b[sb]);                  // hi image of the K tile
                 const uint64_t bl = smem_desc_k128(sm.b[sb] + kTcBTileBytes);  // lo image
@@ -1109,10 +1136,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
         // ===================== B loader (warp-uniform, one elected lane issues the bulk copy) =====================
         const unsigned char *src = reinterpret_cast<const unsigned char *>(Bimg) + (size_t)tj * kKTiles * kTcBStageBytes;
         for (int it = 0; it < kIters; ++it) {
-            const int sb = it % kTcBStages, kt = ((it % kKTiles) + kshift) & (kKTiles - 1);
-            mbar_wait_warp(&sm.empty_a[sb], (uint32_t)(((it / kTcBStages) & 1) ^ 1), 100);
+            const int sb = it % kBS, kt = ((it % kKTiles) + kshift) & (kKTiles - 1);
+            mbar_wait_warp(&sm.empty_a[sb], (uint32_t)(((it / kBS) & 1) ^ 1), 100);
             if (elect_one()) {
-                if (DBG && (dbg & 1) && it >= kTcBStages) {  // timing experiment: no B traffic after the first ring fill
+                if (DBG && (dbg & 1) && it >= kBS) {  // timing experiment: no B traffic after the first ring fill
                     mbar_arrive(&sm.full_b[sb]);
                 } else {
                     mbar_arrive_expect_tx(&sm.full_b[sb], kTcBStageBytes);
@@ -1126,7 +1153,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cqt_tc_kernel(const float *__re
     __syncthreads();
     if (warp == kTcFrameWarps) {
         fence_after_sync();
-        tmem_dealloc(tmem, kTcTmemCols);
+        tmem_dealloc(tmem, CFG::kTmem);
     }
 }
 
@@ -1594,8 +1621,9 @@ extern "C" int ncfa_chroma_mean_batched(const float *d_audio, const int64_t *d_s
         use_tc = (e && strcmp(e, "simt") == 0) ? 0 : 1;
     }
     if ((rc = ensure_dynamic_smem((const void *)cqt_chroma_kernel, sizeof(CqtSmem)))) return rc;
-    if ((rc = ensure_dynamic_smem((const void *)cqt_tc_kernel<false>, sizeof(TcSmem) + 1024))) return rc;
-    if ((rc = ensure_dynamic_smem((const void *)cqt_tc_kernel<true>, sizeof(TcSmem) + 1024))) return rc;
+    if ((rc = ensure_dynamic_smem((const void *)cqt_tc_kernel<false, TcOne>, sizeof(TcSmem) + 1024))) return rc;
+    if ((rc = ensure_dynamic_smem((const void *)cqt_tc_kernel<true, TcOne>, sizeof(TcSmem) + 1024))) return rc;
+    if ((rc = ensure_dynamic_smem((const void *)cqt_tc_kernel<false, TcTwo>, sizeof(TcSmemT<TcTwo::kB, TcTwo::kPre>) + 1024))) return rc;
     if ((rc = ensure_dynamic_smem((const void *)cqt_tc2_kernel, sizeof(TcSmem) + 1024))) return rc;
     const int tiles = chroma_tiles(max_seg_len);  // partial[] stride (sized for the 32-frame tiles of the SIMT kernel)
     if (use_tc) {
@@ -1606,20 +1634,23 @@ extern "C" int ncfa_chroma_mean_batched(const float *d_audio, const int64_t *d_s
             const char *e = getenv("NCFA_TC_DEBUG");  // timing experiments only (results are wrong when non-zero)
             dbg = e ? atoi(e) : 0;
         }
-        static int tc1 = -1;
-        if (tc1 < 0) {
-            const char *e = getenv("NCFA_CQT_IMPL");  // "tc1": the octave-major tensor-core kernel (before/after, cross-check)
-            tc1 = (e && strcmp(e, "tc1") == 0) ? 1 : 0;
+        static int impl = -1;  // 0: two shallow CTAs per SM (default), 1: one deep CTA per SM, 2: the k-tile-major kernel
+        if (impl < 0) {
+            const char *e = getenv("NCFA_CQT_IMPL");  // "tc1" / "tc2": the other tensor-core forms (before/after, cross-checks)
+            impl = (e && strcmp(e, "tc1") == 0) ? 1 : (e && strcmp(e, "tc2") == 0) ? 2 : 0;
         }
         if (dbg)
-            cqt_tc_kernel<true><<<g, kTcThreads, sizeof(TcSmem) + 1024, st>>>(d_audio, d_seg_off, d_seg_len, pyr, po,
-                                                                              d_tuning_idx, ct.Bimg, tiles, partial, dbg);
-        else if (!tc1)
+            cqt_tc_kernel<true, TcOne><<<g, kTcThreads, sizeof(TcSmem) + 1024, st>>>(d_audio, d_seg_off, d_seg_len, pyr, po,
+                                                                                     d_tuning_idx, ct.Bimg, tiles, partial, dbg);
+        else if (impl == 2)
             cqt_tc2_kernel<<<g, kTcThreads, sizeof(TcSmem) + 1024, st>>>(d_audio, d_seg_off, d_seg_len, pyr, po, d_tuning_idx,
                                                                          ct.Bimg, tiles, partial);
+        else if (impl == 1)
+            cqt_tc_kernel<false, TcOne><<<g, kTcThreads, sizeof(TcSmem) + 1024, st>>>(d_audio, d_seg_off, d_seg_len, pyr, po,
+                                                                                      d_tuning_idx, ct.Bimg, tiles, partial, 0);
         else
-            cqt_tc_kernel<false><<<g, kTcThreads, sizeof(TcSmem) + 1024, st>>>(d_audio, d_seg_off, d_seg_len, pyr, po,
-                                                                               d_tuning_idx, ct.Bimg, tiles, partial, 0);
+            cqt_tc_kernel<false, TcTwo><<<g, kTcThreads, sizeof(TcSmemT<TcTwo::kB, TcTwo::kPre>) + 1024, st>>>(
+                d_audio, d_seg_off, d_seg_len, pyr, po, d_tuning_idx, ct.Bimg, tiles, partial, 0);
         NCFA_LAUNCH_OK("cqt_tc_kernel");
     } else {
         ProfScope _p("cqt_chroma_kernel", st);

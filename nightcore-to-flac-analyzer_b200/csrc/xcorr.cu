@@ -374,8 +374,8 @@ __device__ __forceinline__ double consumer_sum(double v, double *sh) {
     return s;
 }
 
-template <int NQ, int G, int CHUNK, int STAGES, int CONSUMERS>
-__global__ void __launch_bounds__(CONSUMERS + 32, 1) xcorr_blocks_ring_kernel(const float *__restrict__ a,
+template <int NQ, int G, int CHUNK, int STAGES, int CONSUMERS, int MINB = 1>
+__global__ void __launch_bounds__(CONSUMERS + 32, MINB) xcorr_blocks_ring_kernel(const float *__restrict__ a,
                                                                        const float *__restrict__ b,
                                                                        const int64_t *__restrict__ a_pos,
                                                                        const int64_t *__restrict__ b_lo,
@@ -495,30 +495,45 @@ __global__ void __launch_bounds__(CONSUMERS + 32, 1) xcorr_blocks_ring_kernel(co
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.empty[st]);   // this warp is done reading the stage
     }
-    double *pw = part + (size_t)w * (kMaxPieces + 1) * max_blocks;
+    // ---- the CTA's (G·(NQ+1) + 1) sums: per-thread partials go through the (now idle) ring memory, then warp v sums
+    // column v in a fixed order — two barriers instead of three per value (the per-value block reductions were 10 % of
+    // the kernel's stall samples, with the copy pipeline drained)
+    constexpr int NV = G * (NQ + 1) + 1;
+    static_assert((size_t)NV * CONSUMERS * sizeof(double) <= sizeof(sm.tile), "reduction scratch must fit in the ring");
+    double *red = reinterpret_cast<double *>(&sm.tile[0][0][0]);
+    asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");  // every consumer is through with the ring
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-        if (g < live) {  // CTA-uniform
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-                const double v = consumer_sum<CONSUMERS>(d[g][q], sh);
-                if (tid == 0) pw[(size_t)q * max_blocks + m0 + g] = v;
-            }
-            const double v = consumer_sum<CONSUMERS>(s2[g], sh);
-            if (tid == 0) pw[(size_t)kMaxPieces * max_blocks + m0 + g] = v;
-        }
+        for (int q = 0; q < NQ; ++q) red[(size_t)(g * (NQ + 1) + q) * CONSUMERS + tid] = d[g][q];
+        red[(size_t)(g * (NQ + 1) + NQ) * CONSUMERS + tid] = s2[g];
     }
     if (blockIdx.x == 0) {
+        // the tail samples [NQ·stride, win) of wa belong to ‖wa‖² too
         for (int i = NQ * stride + tid; i < win; i += CONSUMERS) {
             const double x = (double)__ldg(wa + i);
             sa = fma(x, x, sa);
         }
-        sa = consumer_sum<CONSUMERS>(sa, sh);
-        if (tid == 0) na2[w] = sa;
+    }
+    red[(size_t)(NV - 1) * CONSUMERS + tid] = sa;
+    asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");
+    double *pw = part + (size_t)w * (kMaxPieces + 1) * max_blocks;
+    for (int v = warp; v < NV; v += CONSUMERS / 32) {
+        double acc = 0.0;
+        for (int t = lane; t < CONSUMERS; t += 32) acc += red[(size_t)v * CONSUMERS + t];
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            if (v == NV - 1) {
+                if (blockIdx.x == 0) na2[w] = acc;
+            } else {
+                const int g = v / (NQ + 1), q = v - g * (NQ + 1);
+                if (g < live) pw[(size_t)(q == NQ ? kMaxPieces : q) * max_blocks + m0 + g] = acc;
+            }
+        }
     }
 }
 
-// ---- ring form with the A blocks in registers (the default) ------------------------------------------------------------
+// ---- ring form with the A blocks in registers (experiment, NCFA_XCORR_IMPL=areg) ----------------------------------------
 // ncu on the ring kernel above (profiles/r2i: 4 or 8 B blocks per CTA, 2 KB / 4 KB / 8 KB copies, 3-6 stages, one or two
 // CTAs per SM) always lands on the same ~18 B/clk of bulk-copy traffic per SM with the consumers waiting on the full
 // barriers, i.e. the copy engine of an SM sustains only so many bytes in flight; what counts is how many of those bytes
@@ -926,11 +941,19 @@ static bool xcorr_g4() {
     }();
     return v;
 }
-// NCFA_XCORR_IMPL=ring8: eight B blocks per CTA with the A blocks in the ring too (before/after of the register-A default)
-static bool xcorr_ring8() {
+// NCFA_XCORR_IMPL=x2: eight B blocks per CTA, 512-sample chunks, two CTAs per SM (register-capped at 112)
+static bool xcorr_x2() {
     static const bool v = [] {
         const char *e = getenv("NCFA_XCORR_IMPL");
-        return e && strcmp(e, "ring8") == 0;
+        return e && strcmp(e, "x2") == 0;
+    }();
+    return v;
+}
+// NCFA_XCORR_IMPL=areg: the A blocks through registers, only the B blocks in the ring (measured slower: 2.45 vs 2.7 TB/s)
+static bool xcorr_areg() {
+    static const bool v = [] {
+        const char *e = getenv("NCFA_XCORR_IMPL");
+        return e && strcmp(e, "areg") == 0;
     }();
     return v;
 }
@@ -988,7 +1011,14 @@ extern "C" int ncfa_xcorr_search_batched(const float *d_a, const float *d_b, con
                 int rc = 0;
 #define NCFA_XR_LAUNCH(NQ_)                                                                                             \
     do {                                                                                                                \
-        if (!xcorr_g4() && !xcorr_ring8()) {                                                                            \
+        if (xcorr_x2()) {                                                                                               \
+            using Sm = XrSmem<NQ_, 8, 512, 4, 256>;                                                                     \
+            auto kfn = xcorr_blocks_ring_kernel<NQ_, 8, 512, 4, 256, 2>;                                                \
+            if ((rc = ensure_dynamic_smem((const void *)kfn, sizeof(Sm)))) return rc;                                   \
+            dim3 g8((max_cand + nq - 1 + 7) / 8, n_windows);                                                            \
+            kfn<<<g8, 256 + 32, sizeof(Sm), st>>>(d_a, d_b, d_a_pos, d_b_lo, d_n_cand, max_blocks, win, stride, part,   \
+                                                  na2b);                                                                \
+        } else if (xcorr_areg()) {                                                                                      \
             using Sm = XaSmem<8, 1024, 6>;                                                                              \
             auto kfn = xcorr_blocks_areg_kernel<NQ_, 8, 1024, 6, 256>;                                                  \
             if ((rc = ensure_dynamic_smem((const void *)kfn, sizeof(Sm)))) return rc;                                   \

@@ -136,13 +136,15 @@ def analyse_staged(batch: StagedBatch, *, window_sec: float = WINDOW_SEC, hop_se
 
     # ---- stage 2: windows, float64 energies, gate (io.py:82-126)
     win_n, hop_n = int(window_sec * sr), int(hop_sec * sr)
-    seg_track, seg_off = [], []
-    for k in range(n_tracks):
-        st = _window_starts(int(t_len[k]), win_n, hop_n)
-        seg_track.append(np.full(len(st), k, dtype=np.int64))
-        seg_off.append(t_off[k] + st)
-    seg_track = np.concatenate(seg_track) if seg_track else np.zeros(0, np.int64)
-    seg_off = np.concatenate(seg_off) if seg_off else np.zeros(0, np.int64)
+    # io.py:94-110 for every track at once: starts 0, hop_n, … while start + win_n <= n  (same values as _window_starts)
+    if win_n > 0 and hop_n > 0 and n_tracks:
+        tl = t_len.astype(np.int64)
+        n_w = np.where(tl >= win_n, (tl - win_n) // hop_n + 1, 0)
+        seg_track = np.repeat(np.arange(n_tracks, dtype=np.int64), n_w)
+        within = np.arange(int(n_w.sum()), dtype=np.int64) - np.repeat(np.cumsum(n_w) - n_w, n_w)
+        seg_off = t_off.astype(np.int64)[seg_track] + within * hop_n
+    else:
+        seg_track, seg_off = np.zeros(0, np.int64), np.zeros(0, np.int64)
     seg_len = np.full(len(seg_off), win_n, dtype=np.int32)
     if len(seg_off):
         ms = eng.window_energy_dev(batch.audio, eng.to_dev(seg_off), eng.to_dev(seg_len)).cpu().numpy()
@@ -215,7 +217,7 @@ def analyse_staged(batch: StagedBatch, *, window_sec: float = WINDOW_SEC, hop_se
     for i in range(P):
         valid = [t for t in src_tempos[i] if t is not None]
         if valid and nc_dur[i] > 0 and src_dur[i] > 0:
-            prior[i] = float(np.median(valid)) * (src_dur[i] / nc_dur[i])
+            prior[i] = consensus._median_small(valid) * (src_dur[i] / nc_dur[i])
 
     # ---- stage 6: nightcore windows with the pair's prior
     sel_nc = np.flatnonzero(keep & ~is_src & alive[pair_of])
@@ -316,6 +318,17 @@ def plan_subbatches(n_pairs: int, sub: int, workers: int = 2, first: int = 8, gr
     return sizes
 
 
+def _first_job_pairs(n_pairs: int, sub: int) -> int:
+    """Size of the first streamed job.  Its upload is the only one nothing hides, so it should be small; but jobs of a
+    few pairs are latency bound on the device (one CTA per envelope in the beat tracker, short grids), so it should not
+    be tiny either.  NCFA_E2E_FIRST overrides (experiments)."""
+    import os
+    env = os.environ.get("NCFA_E2E_FIRST")
+    if env:
+        return max(1, int(env))
+    return 8   # measured on B200, 1000 pairs (profiles/r2l): first = 8 → 1107 pairs/s end to end, 24 → 913, 48 → 891, 83 → 890
+
+
 # ------------------------------------------------------------------------------------------------ the batch scheduler
 # One stager thread walks the jobs (consecutive, disjoint slices of the batch) in order: it lays a slice out in pinned
 # memory when the caller's arrays are pageable, queues its host→HBM copy on a copy stream into one of `workers + 1`
@@ -384,12 +397,14 @@ def analyse_batch(source, sr: int = SAMPLE_RATE, *, sub_batch: int = SUB_BATCH_P
     if P == 0:
         return []
     if sizes is None:
-        sizes = [P] if P <= INLINE_PAIRS else plan_subbatches(P, sub_batch, workers)
+        sizes = [P] if P <= INLINE_PAIRS else plan_subbatches(P, sub_batch, workers, first=_first_job_pairs(P, sub_batch))
     sizes = [int(k) for k in sizes]
     if any(k <= 0 for k in sizes) or sum(sizes) != P:
         raise ValueError(f"sub-batch sizes {sizes} do not cover the {P} pairs of the batch exactly once")
     starts = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(int)
 
+    if stats is not None:
+        stats["sub_batches"] = list(sizes)
     if len(sizes) == 1:      # one pass in the calling thread
         st = upload(source) if pinned_in else stage_pairs(list(source), sr)
         s1: dict = {}

@@ -129,8 +129,19 @@ class AnalysisResult:
 # ── internals ────────────────────────────────────────────────────────────────
 def _valid(values: Sequence[Optional[float]]) -> np.ndarray:
     """consensus.py:236-240 — drop None / non-finite / non-positive entries."""
-    keep = [v for v in values if v is not None and np.isfinite(v) and v > 0]
+    isfinite = math.isfinite      # same predicate as np.isfinite on a Python / numpy scalar, a tenth of the cost
+    keep = [v for v in values if v is not None and isfinite(v) and v > 0]
     return np.array(keep, dtype=np.float64)
+
+
+def _median_small(values) -> float:
+    """np.median of a short 1-D sequence of finite float64 values, bit for bit (middle element, or the mean of the two
+    middle elements computed as (a + b) / 2 like np.mean of two values) without numpy's per-call overhead — the batch
+    path takes a few medians per pair, 150 µs of interpreter time each way through np.median."""
+    v = sorted(float(x) for x in values)
+    n = len(v)
+    h = n >> 1
+    return v[h] if n & 1 else (v[h - 1] + v[h]) / 2.0
 
 
 def _percentile_args(ci: float) -> Tuple[float, float]:
@@ -324,8 +335,8 @@ def _assemble(src_pitches, nc_pitches, src_tempos, nc_tempos, src_t, nc_t, pitch
         rubberband=_rubberband_params(tempo_ratio, pitch_ratio, nc_duration, src_duration),
         nc_duration=nc_duration,
         src_duration=src_duration,
-        nc_median_bpm=float(np.median(nc_t)) if len(nc_t) > 0 else None,
-        src_median_bpm=float(np.median(src_t)) if len(src_t) > 0 else None,
+        nc_median_bpm=_median_small(nc_t) if len(nc_t) > 0 else None,
+        src_median_bpm=_median_small(src_t) if len(src_t) > 0 else None,
         warnings=_check_sanity(tempo_ratio, pitch_ratio, tempo_ci, pitch_ci, nc_duration, src_duration, flipped),
         src_pitches_raw=list(src_pitches),
         nc_pitches_raw=list(nc_pitches),

@@ -55,3 +55,16 @@ def test_classify_thresholds():
     assert c._classify(1.0, 1.1, (0.99, 1.01), (1.09, 1.11)) == "independent_pitch_shift"
     assert c._classify(1.0, 0.9, (0.99, 1.01), (0.89, 0.91)) == "ambiguous"
     assert c._classify(1.25, 1.28, (1.2, 1.3), (1.2, 1.3)) == "pure_nightcore"      # overlapping CIs, diff <= 2·tol
+
+
+def test_small_median_is_np_median_bit_for_bit():
+    """batch.analyse_staged and consensus._assemble take their per-pair medians through consensus._median_small."""
+    import numpy as np
+    from nightcore_analyzer import consensus
+    rng = np.random.default_rng(3)
+    for _ in range(5000):
+        a = rng.uniform(40.0, 260.0, int(rng.integers(1, 48)))
+        if rng.random() < 0.4:
+            a = np.round(a, 1)          # ties, as quantised BPM values produce them
+        assert consensus._median_small(a) == float(np.median(a))
+    assert consensus._median_small([3.0, 1.0]) == 2.0
