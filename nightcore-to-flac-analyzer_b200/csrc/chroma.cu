@@ -745,26 +745,24 @@ __global__ void __launch_bounds__(kCqtThreads) cqt_chroma_kernel(const float *__
 
 // ------------------------------------------------------------------------------------------------ CQT on tcgen05
 // Same contraction on the 5th-generation tensor cores:  D[128 frames × 80] (+)= A[128 × 8]·B[80 × 8]^T, kind::tf32,
-// with the 3×TF32 split  x = hi + lo  (hi = rna_tf32(x), lo = x − hi exactly):  A·B ≈ Ah·Bh + Al·Bh + Ah·Bl.
-// Timing experiments (NCFA_TC_DEBUG) showed the MMAs are almost free next to the producer ↔ issuer handshake, whose
-// cost is set by how many A stages are in flight — so tensor memory goes to a 5-deep A ring (320 columns) and two
-// narrow accumulators (2 × 80), rather than to wide N-stacked accumulators.
-//   A (the Hankel matrix of frames) is never materialised in memory: frame thread f keeps row f, reads its 32 samples of
-//     the k-tile straight from global memory (L1/L2 serve the overlap between frames), splits them in registers and
-//     writes hi / lo into TENSOR MEMORY with tcgen05.st; the MMA reads A from TMEM (TS form).
+// with the 3×TF32 split  x = hi + lo  (hi = x truncated to tf32, lo = x − hi exactly):  A·B ≈ Ah·Bh + Al·Bh + Ah·Bl.
+//   A (the Hankel matrix of frames) is never materialised in memory: the frame warps stage the rows of a k-tile in shared
+//     memory with coalesced cp.async copies (64 contiguous bytes of eight rows per instruction; L1/L2 serve the overlap
+//     between frames), every frame thread then reads its own row piece, splits it in registers and writes hi / lo into
+//     TENSOR MEMORY with tcgen05.st; the MMA reads A from TMEM (TS form).
 //   B (the folded CQT matrix) is pre-split and pre-swizzled on the host as shared-memory images, so a k-tile is ONE
 //     20 KB 1-D bulk async copy (cp.async.bulk + mbarrier complete_tx) — no tensor map needed.
-//   D lives in TMEM, double buffered across octaves; the epilogue (tcgen05.ld → |re + i·im| → fold to 12 chroma) of
-//     octave o−1 overlaps the MMAs of octave o.
-// Warp roles (576 threads): warps 0-15 frame warps (A producer + epilogue; warp w serves rows 32·(w & 3) … +31 — its
-// TMEM lane quarter — and column quarter q = w >> 2 of every k-tile, so four warps per scheduler hide each other's
-// latencies), warp 16 MMA issuer and TMEM allocator, warp 17 B loader.  Pipelines: A ring (5 stages in TMEM, fed through
-// a 4-deep cp.async ring in shared memory), B ring (6 stages in shared memory), accumulator ring (2).
+//   D lives in TMEM; the epilogue is tcgen05.ld → |re + i·im| → fold to 12 chroma.
+// Warp roles (320 threads): warps 0-7 frame warps (A producer + epilogue; warp w serves rows 32·(w & 3) … +31 — its TMEM
+// lane quarter — and column half q = w >> 2 of every k-tile), warp 8 MMA issuer and TMEM allocator, warp 9 B loader.
+// Pipeline shape (struct TcOne / TcTwo below): the default is TWO CTAs per SM, each with 2 A stages, 2 B images, one
+// accumulator and 256 TMEM columns; NCFA_CQT_IMPL=tc1 selects one CTA per SM with 5 A stages, 5 B images and two
+// accumulators (epilogue of octave o−1 overlapped with the MMAs of octave o+1).
 constexpr int kTcFrames = 128;
 constexpr int kTcQ = 2;                                  // column splits of a k-tile row (threads per frame row)
 constexpr int kTcVals = kTcKT / kTcQ;                    // samples per thread per k-tile (16)
 constexpr int kTcFrameWarps = 4 * kTcQ;
-constexpr int kTcThreads = (kTcFrameWarps + 2) * 32;     // 576
+constexpr int kTcThreads = (kTcFrameWarps + 2) * 32;     // 320
 constexpr int kTcAStages = 5;
 constexpr int kTcBStages = kTcAStages;                   // A and B share the stage index and ONE release barrier per stage
 constexpr int kTcACols = 2 * kTcKT;                      // hi + lo columns of one A stage
@@ -792,7 +790,10 @@ using TcSmem = TcSmemT<kTcBStages>;
 // 2 B images, one accumulator, 256 TMEM columns, 107 KB of shared memory).  The timing experiments (NCFA_TC_DEBUG,
 // profiles/r2l_cqt_debug.log) show that with A traffic, B traffic AND the MMAs all switched off the kernel still takes
 // 12.3 of its 13.4 ms: what paces it is the latency of one CTA's serial producer → MMA → release chain, with two or three
-// warps per scheduler to hide it.  A second resident CTA overlaps two such chains on the same tensor pipe.
+// warps per scheduler to hide it.  A second resident CTA overlaps two such chains on the same tensor pipe: 13.4 -> 9.8 ms
+// per 1750 chunks (profiles/r2m).  (A k-tile-major variant that fetched every B image once per four octaves — 3.5x less
+// bulk-copy traffic — measured exactly the same 13.4 ms as the octave-major order and was dropped: B traffic is not the
+// limiter either.)
 struct TcOne {
     static constexpr int kA = kTcAStages, kB = kTcBStages, kAcc = 2, kTmem = 512, kMinBlocks = 1, kPre = kTcAPre;
 };
@@ -1157,319 +1158,6 @@ __global__ void __launch_bounds__(kTcThreads, CFG::kMinBlocks) cqt_tc_kernel(con
     }
 }
 
-// ---- k-major form (the default) ------------------------------------------------------------------------------------------
-// The CQT matrix is the SAME for every octave (only the signal level changes), and the kernel above walks octave-major: each
-// 20 KB B image is fetched once per (octave, k-tile) — 4.5 MB of bulk copies per CTA, 13 B/clk/SM at the measured rate, and
-// ncu shows the frame warps waiting for A stages to be released, i.e. for MMAs that wait for B (profiles/r2i: tensor pipe
-// 36 %; a single SM's copy engine sustained ~18 B/clk in the waveform-xcorr kernel).  Here the loop is k-tile-major:
-// one B image serves the k-tile's MMAs of FOUR octaves (pass 0: octaves 0-3, four 80-column accumulators) and then of THREE
-// (pass 1: octaves 4-6) — B traffic drops 3.5x to 1.3 MB per CTA.  TMEM: 320 accumulator columns + a 3-stage A ring (192).
-// Everything else — the coalesced cp.async staging of the Hankel rows, the truncation split, tcgen05.st, the 3xTF32
-// products, the epilogue arithmetic and its summation order per octave — is unchanged, so the chroma values are those of
-// the octave-major kernel up to the order in which the seven octaves' magnitudes are added.
-constexpr int kT2AStages = 3;
-constexpr int kT2AccCols = 4 * kTcN;                 // 320: accumulators of up to four octaves
-constexpr int kT2ACol0 = kT2AccCols;                 // A ring: 3 stages × (hi 32 + lo 32) columns
-constexpr int kT2Pass0 = 4 * (kCqtNfft / kTcKT);     // iterations of pass 0 (4 octaves × 32 k-tiles)
-static_assert(kT2ACol0 + kT2AStages * kTcACols <= 512, "TMEM budget");
-
-// flat iteration → (pass, k-tile step, octave-in-pass, octave)
-__device__ __forceinline__ void t2_decode(int it, int &p, int &kk, int &oi, int &o) {
-    if (it < kT2Pass0) {
-        p = 0;
-        kk = it >> 2;
-        oi = it & 3;
-        o = oi;
-    } else {
-        const int r = it - kT2Pass0;
-        p = 1;
-        kk = r / 3;
-        oi = r - 3 * kk;
-        o = 4 + oi;
-    }
-}
-
-__global__ void __launch_bounds__(kTcThreads, 1) cqt_tc2_kernel(const float *__restrict__ audio,
-                                                                const int64_t *__restrict__ seg_off,
-                                                                const int32_t *__restrict__ seg_len,
-                                                                const float *__restrict__ pyr, PyrOffsets po,
-                                                                const int32_t *__restrict__ tuning_idx,
-                                                                const float *__restrict__ Bimg, int tile_stride,
-                                                                double *__restrict__ partial) {
-    using namespace tc05;
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    TcSmem &sm = *reinterpret_cast<TcSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int seg = blockIdx.y;
-    const int n = seg_len[seg];
-    const int n_frames = cqt_frames(n);
-    const int t0 = blockIdx.x * kTcFrames;
-    if (t0 >= n_frames) return;  // whole CTA leaves before any barrier / TMEM state exists
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-    if (tid == 0) {
-        for (int i = 0; i < kT2AStages; ++i) {
-            mbar_init(&sm.full_a[i], kTcFrameWarps);  // one arrival per frame warp
-            mbar_init(&sm.empty_a[i], 1);
-        }
-        for (int i = 0; i < kTcBStages; ++i) {
-            mbar_init(&sm.full_b[i], 1);
-            mbar_init(&sm.empty_b[i], 1);
-        }
-        mbar_init(&sm.acc_full[0], 1);
-        mbar_init(&sm.acc_empty[0], kTcFrameWarps);
-        fence_mbar_init();
-    }
-    if (warp == kTcFrameWarps) tmem_alloc(&sm.tmem_base, kTcTmemCols);
-    fence_before_sync();
-    __syncthreads();
-    fence_after_sync();
-    const uint32_t tmem = sm.tmem_base;
-
-    int tj = tuning_idx[seg];
-    tj = tj < 0 ? 0 : (tj >= kNTunings ? kNTunings - 1 : tj);
-    constexpr int kKTiles = kCqtNfft / kTcKT;  // 32
-    constexpr int kIters = kOctaves * kKTiles;
-    // every CTA starts its walk over the 32 k-tiles at a different tile (all CTAs of a launch read the same few B images)
-    const int kshift = (int)((blockIdx.x * 5u + blockIdx.y * 11u) & (kKTiles - 1));
-
-    if (warp < kTcFrameWarps) {
-        // ===================== frame warps: A producer + epilogue =====================
-        const int rg = warp & 3, q = warp >> 2;   // TMEM lane quarter, column split
-        const int f = 32 * rg + lane;  // row of the tile = TMEM lane
-        const uint32_t lane_base = (uint32_t)(32 * rg) << 16;
-        const float *pseg = pyr + (size_t)seg * po.off[kOctaves];
-        constexpr int kQPer = 4 / kTcQ;  // epilogue quarters (9 CQT bins each) per thread
-        float part[kQPer][4];
-#pragma unroll
-        for (int a = 0; a < kQPer; ++a)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) part[a][j] = 0.0f;
-
-        auto epilogue = [&](int p) {  // the pass's accumulators, in octave order
-            mbar_wait_warp(&sm.acc_full[0], (uint32_t)(p & 1), 100);
-            fence_after_sync();
-            const int n_oct = p == 0 ? 4 : 3;
-            for (int oi = 0; oi < n_oct; ++oi) {
-                const uint32_t acc = tmem + lane_base + (uint32_t)(oi * kTcN);
-#pragma unroll
-                for (int a = 0; a < kQPer; ++a) {
-                    switch (q * kQPer + a) {  // warp-uniform
-                        case 0: tc_epilogue_quarter<0>(acc, part[a]); break;
-                        case 1: tc_epilogue_quarter<1>(acc, part[a]); break;
-                        case 2: tc_epilogue_quarter<2>(acc, part[a]); break;
-                        default: tc_epilogue_quarter<3>(acc, part[a]); break;
-                    }
-                }
-            }
-            fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.acc_empty[0]);
-        };
-
-        constexpr int kChunks = kTcVals / 4;
-        static_assert(kChunks == 4, "lane mapping below assumes 4 chunks per row half");
-        const float *y0 = audio + seg_off[seg];
-        const bool y0_aligned = (reinterpret_cast<uintptr_t>(y0) & 15u) == 0;
-        const float *y0_down = reinterpret_cast<const float *>(reinterpret_cast<uintptr_t>(y0) & ~uintptr_t(15));
-        const int r8 = lane >> 2, cc = lane & 3;
-        const int frow = t0 + 32 * rg + r8;                 // first of the four rows (8 apart) this lane fetches
-        const int coff = -kCqtNfft / 2 + kTcVals * q + 4 * cc;  // its 16-byte piece inside a k-tile, centred frames
-        // per octave, warp-uniform: can the copies of this warp skip the edge clamping?  (bit o of fastmask)
-        unsigned fastmask = 0;
-#pragma unroll
-        for (int o = 0; o < kOctaves; ++o) {
-            const int hop = 512 >> o;
-            const int len_o = (n + (1 << o) - 1) >> o;  // = level_len(n, o)
-            const int row0 = frow * hop + coff;
-            const bool inside = row0 >= 0 && row0 + 24 * hop + (kCqtNfft - kTcKT) + 4 <= len_o;
-            const bool ok = ((o > 0) || y0_aligned) && __all_sync(0xffffffffu, inside);
-            fastmask |= ok ? (1u << o) : 0u;
-        }
-        const uint32_t arow_u32 = smem_u32(&sm.arow[0][0]);
-        const uint32_t slot_off = (uint32_t)(((kChunks * q + cc) * kTcAPlane + 32 * rg + r8) * sizeof(float4));
-        constexpr uint32_t kSlotBytes = 8 * kTcAPlane * sizeof(float4);
-        auto issue = [&](int it) {
-            int p, kk, oi, o;
-            t2_decode(it, p, kk, oi, o);
-            const int kt = (kk + kshift) & 31;
-            const int hop = 512 >> o;
-            const float *ylev = (o == 0) ? y0 : pseg + po.off[o];
-            const int row_step = 8 * hop;
-            const int p0 = frow * hop + coff + kt * kTcKT;
-            const uint32_t slot_u32 = arow_u32 + (uint32_t)(it % kTcAPre) * kSlotBytes + slot_off;
-            if ((fastmask >> o) & 1u) {
-                const float *src = ylev + p0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(slot_u32 + (uint32_t)(8 * j * sizeof(float4))),
-                                 "l"(src + j * row_step)
-                                 : "memory");
-            } else if ((o > 0) || y0_aligned) {
-                const int len_o = (n + (1 << o) - 1) >> o;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int pp = p0 + j * row_step;  // first sample of this 16-byte piece (multiple of 4: never straddles 0)
-                    const int rem = (len_o - pp) * 4;
-                    const uint32_t bytes = (pp < 0 || rem <= 0) ? 0u : (uint32_t)(rem > 16 ? 16 : rem);
-                    const float *src = bytes ? ylev + pp : y0_down;  // src-size 0: nothing is read, but the address stays aligned
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(slot_u32 + (uint32_t)(8 * j * sizeof(float4))),
-                                 "l"(src), "r"(bytes)
-                                 : "memory");
-                }
-            } else {  // unaligned first level (arbitrary caller offset): plain loads into the same slots
-                const int len_o = n;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float xr[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int pp = p0 + j * row_step + i;
-                        xr[i] = (pp >= 0 && pp < len_o) ? __ldg(ylev + pp) : 0.0f;
-                    }
-                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot_u32 + (uint32_t)(8 * j * sizeof(float4))),
-                                 "f"(xr[0]), "f"(xr[1]), "f"(xr[2]), "f"(xr[3])
-                                 : "memory");
-                }
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        for (int it = 0; it < kTcAPre - 1; ++it) issue(it);
-        bool pending = false;
-        for (int it = 0; it < kIters; ++it) {
-            if (it + kTcAPre - 1 < kIters) issue(it + kTcAPre - 1);
-            else asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group %0;" ::"n"(kTcAPre - 1) : "memory");
-            __syncwarp();  // the row this thread reads was fetched by other lanes of its warp
-            const int st = it % kT2AStages;
-            uint32_t h[kTcVals], l[kTcVals];
-            {
-                // x = hi + lo, hi = x truncated to tf32 (one LOP3), lo = x − hi exactly (see the octave-major kernel)
-                const uint32_t rd = arow_u32 + (uint32_t)(it % kTcAPre) * kSlotBytes +
-                                    (uint32_t)(((kChunks * q) * kTcAPlane + f) * sizeof(float4));
-#pragma unroll
-                for (int c = 0; c < kChunks; ++c) {
-                    float x[4];
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                 : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3])
-                                 : "r"(rd + (uint32_t)(c * kTcAPlane * sizeof(float4)))
-                                 : "memory");
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const uint32_t hb = __float_as_uint(x[i]) & 0xffffe000u;
-                        h[4 * c + i] = hb;
-                        l[4 * c + i] = __float_as_uint(x[i] - __uint_as_float(hb));
-                    }
-                }
-            }
-            __syncwarp();  // all lanes have read the slot before other lanes re-fill it (issue() of the next iteration)
-            if (pending) {  // publish the PREVIOUS tile: its tcgen05.st had a whole iteration to land
-                wait_st();
-                fence_before_sync();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.full_a[(it - 1) % kT2AStages]);
-            }
-            mbar_wait_warp(&sm.empty_a[st], (uint32_t)(((it / kT2AStages) & 1) ^ 1), 40);
-            fence_after_sync();
-            const uint32_t a0 = tmem + lane_base + (uint32_t)(kT2ACol0 + st * kTcACols + kTcVals * q);
-            tmem_st_vals(a0, h);
-            tmem_st_vals(a0 + kTcKT, l);
-            pending = true;
-            if (it == kT2Pass0 - 1 || it == kIters - 1) {  // end of a pass: publish, then read the pass's accumulators
-                wait_st();
-                fence_before_sync();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.full_a[st]);
-                pending = false;
-                epilogue(it == kIters - 1 ? 1 : 0);
-            }
-        }
-
-        // ---- combine the four column quarters of every frame, librosa.util.normalize(norm=inf) per frame, then the
-        // tile's sum over frames (float64)
-#pragma unroll
-        for (int a = 0; a < kQPer; ++a)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) sm.chroma_part[f][4 * (q * kQPer + a) + j] = part[a][j];
-        asm volatile("bar.sync 1, %0;" ::"n"(kTcFrameWarps * 32) : "memory");  // the frame warps only
-        if (q == 0) {
-            float chroma[kChroma];
-#pragma unroll
-            for (int c = 0; c < kChroma; ++c) {
-                // chroma c = slot j = c % 3 of quarter c / 3, plus slot 3 of the previous quarter when c % 3 == 0
-                float v = sm.chroma_part[f][4 * (c / 3) + (c % 3)];
-                if (c % 3 == 0) v += sm.chroma_part[f][4 * ((c / 3 + 3) % 4) + 3];
-                chroma[c] = v;
-            }
-            const bool valid = (t0 + f) < n_frames;
-            float mx = 0.0f;
-#pragma unroll
-            for (int c = 0; c < kChroma; ++c) mx = fmaxf(mx, chroma[c]);
-            const double len_ = (mx < 1.17549435e-38f) ? 1.0 : (double)mx;
-#pragma unroll
-            for (int c = 0; c < kChroma; ++c) {
-                double v = valid ? (double)chroma[c] / len_ : 0.0;
-                v = warp_sum(v);
-                if (lane == 0) sm.red[rg][c] = v;
-            }
-            asm volatile("bar.sync 2, 128;" ::: "memory");  // warps 0-3
-            if (tid < kChroma)
-                partial[((size_t)seg * tile_stride + blockIdx.x) * kChroma + tid] =
-                    ((sm.red[0][tid] + sm.red[1][tid]) + sm.red[2][tid]) + sm.red[3][tid];
-        }
-    } else if (warp == kTcFrameWarps) {
-        // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
-        constexpr uint32_t idesc = idesc_tf32(kTcFrames, kTcN);  // M 128 × N 80 × K 8
-        for (int it = 0; it < kIters; ++it) {
-            int p, kk, oi, o;
-            t2_decode(it, p, kk, oi, o);
-            const int n_oct = p == 0 ? 4 : 3;
-            const int bseq = p * kKTiles + kk;          // which B image of the CTA's 64
-            const int sa = it % kT2AStages, sb = bseq % kTcBStages;
-            if (it == kT2Pass0) {  // pass 1 overwrites the accumulators of pass 0: its epilogue must be through
-                mbar_wait_warp(&sm.acc_empty[0], 0u);
-            }
-            mbar_wait_warp(&sm.full_a[sa], (uint32_t)((it / kT2AStages) & 1));
-            if (oi == 0) mbar_wait_warp(&sm.full_b[sb], (uint32_t)((bseq / kTcBStages) & 1));
-            fence_after_sync();
-            const uint32_t d = tmem + (uint32_t)(oi * kTcN);
-            const uint64_t bh = smem_desc_k128(sm.b[sb]);                  // hi image of the K tile
-            const uint64_t bl = smem_desc_k128(sm.b[sb] + kTcBTileBytes);  // lo image
-            const uint32_t ah = tmem + (uint32_t)(kT2ACol0 + sa * kTcACols), al = ah + kTcKT;
-            if (elect_one()) {
-#pragma unroll
-                for (int k = 0; k < kTcKT / 8; ++k) {
-                    const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 32 bytes per K = 8 step inside the swizzle row
-                    mma_tf32_ts(d, ah + 8 * k, bh + adv, idesc, (kk | k) != 0);  // 3×TF32: Ah·Bh + Al·Bh + Ah·Bl
-                    mma_tf32_ts(d, al + 8 * k, bh + adv, idesc, 1);
-                    mma_tf32_ts(d, ah + 8 * k, bl + adv, idesc, 1);
-                }
-                commit(&sm.empty_a[sa]);                          // frees the A stage (TMEM)
-                if (oi == n_oct - 1) commit(&sm.empty_b[sb]);     // the B image has served all octaves of the pass
-                if (oi == n_oct - 1 && kk == kKTiles - 1) commit(&sm.acc_full[0]);
-            }
-            __syncwarp();
-        }
-    } else {
-        // ===================== B loader (warp-uniform, one elected lane issues the bulk copy) =====================
-        const unsigned char *src = reinterpret_cast<const unsigned char *>(Bimg) + (size_t)tj * kKTiles * kTcBStageBytes;
-        for (int bseq = 0; bseq < 2 * kKTiles; ++bseq) {
-            const int sb = bseq % kTcBStages, kt = ((bseq & (kKTiles - 1)) + kshift) & (kKTiles - 1);
-            mbar_wait_warp(&sm.empty_b[sb], (uint32_t)(((bseq / kTcBStages) & 1) ^ 1), 100);
-            if (elect_one()) {
-                mbar_arrive_expect_tx(&sm.full_b[sb], kTcBStageBytes);
-                bulk_g2s(sm.b[sb], src + (size_t)kt * kTcBStageBytes, kTcBStageBytes, &sm.full_b[sb]);
-            }
-            __syncwarp();
-        }
-    }
-    fence_before_sync();
-    __syncthreads();
-    if (warp == kTcFrameWarps) {
-        fence_after_sync();
-        tmem_dealloc(tmem, kTcTmemCols);
-    }
-}
-
 // mean over frames: one warp per segment sums the tile partials in tile order
 __global__ void __launch_bounds__(32) chroma_mean_kernel(const int32_t *__restrict__ seg_len, int tile_stride,
                                                          int frames_per_tile, const double *__restrict__ partial,
@@ -1624,7 +1312,6 @@ extern "C" int ncfa_chroma_mean_batched(const float *d_audio, const int64_t *d_s
     if ((rc = ensure_dynamic_smem((const void *)cqt_tc_kernel<false, TcOne>, sizeof(TcSmem) + 1024))) return rc;
     if ((rc = ensure_dynamic_smem((const void *)cqt_tc_kernel<true, TcOne>, sizeof(TcSmem) + 1024))) return rc;
     if ((rc = ensure_dynamic_smem((const void *)cqt_tc_kernel<false, TcTwo>, sizeof(TcSmemT<TcTwo::kB, TcTwo::kPre>) + 1024))) return rc;
-    if ((rc = ensure_dynamic_smem((const void *)cqt_tc2_kernel, sizeof(TcSmem) + 1024))) return rc;
     const int tiles = chroma_tiles(max_seg_len);  // partial[] stride (sized for the 32-frame tiles of the SIMT kernel)
     if (use_tc) {
         ProfScope _p("cqt_tc_kernel", st);
@@ -1634,17 +1321,14 @@ extern "C" int ncfa_chroma_mean_batched(const float *d_audio, const int64_t *d_s
             const char *e = getenv("NCFA_TC_DEBUG");  // timing experiments only (results are wrong when non-zero)
             dbg = e ? atoi(e) : 0;
         }
-        static int impl = -1;  // 0: two shallow CTAs per SM (default), 1: one deep CTA per SM, 2: the k-tile-major kernel
+        static int impl = -1;  // 0: two shallow CTAs per SM (default), 1: one deep CTA per SM
         if (impl < 0) {
-            const char *e = getenv("NCFA_CQT_IMPL");  // "tc1" / "tc2": the other tensor-core forms (before/after, cross-checks)
-            impl = (e && strcmp(e, "tc1") == 0) ? 1 : (e && strcmp(e, "tc2") == 0) ? 2 : 0;
+            const char *e = getenv("NCFA_CQT_IMPL");  // "tc1": the one-CTA-per-SM pipeline shape (before/after, cross-check)
+            impl = (e && strcmp(e, "tc1") == 0) ? 1 : 0;
         }
         if (dbg)
             cqt_tc_kernel<true, TcOne><<<g, kTcThreads, sizeof(TcSmem) + 1024, st>>>(d_audio, d_seg_off, d_seg_len, pyr, po,
                                                                                      d_tuning_idx, ct.Bimg, tiles, partial, dbg);
-        else if (impl == 2)
-            cqt_tc2_kernel<<<g, kTcThreads, sizeof(TcSmem) + 1024, st>>>(d_audio, d_seg_off, d_seg_len, pyr, po, d_tuning_idx,
-                                                                         ct.Bimg, tiles, partial);
         else if (impl == 1)
             cqt_tc_kernel<false, TcOne><<<g, kTcThreads, sizeof(TcSmem) + 1024, st>>>(d_audio, d_seg_off, d_seg_len, pyr, po,
                                                                                       d_tuning_idx, ct.Bimg, tiles, partial, 0);

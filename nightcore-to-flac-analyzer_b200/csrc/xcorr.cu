@@ -11,10 +11,11 @@
 // j .. j+3 (plus a tail of win − 4·stride <= 3 samples): with D[q][m] = <A block q, B block m> and
 // S[m] = ‖B block m‖²,
 //     dot(wa, wb_j) = D[0][j] + D[1][j+1] + D[2][j+2] + D[3][j+3] (+ tail),   ‖wb_j‖² = S[j] + ... + S[j+3] (+ tail).
-// xcorr_blocks_kernel gives a CTA one window and kBlocksPerCta consecutive B blocks; a thread walks the
-// sample index i (coalesced), keeps the partial sums of its blocks in registers and loads the four A
-// samples of index i once for all of them — every B sample is read from HBM/L2 ONCE and used in five
-// float64 FMAs, every A sample once per CTA of its window (L2).  xcorr_pick_kernel adds the partials in
+// xcorr_blocks_ring_kernel gives a CTA one window and G = 8 consecutive B blocks; a consumer thread walks the
+// sample index i, keeps the 8 x 5 partial sums of its blocks in registers and reads the four A samples of
+// index i once for all of them — every B sample is read from HBM ONCE and used in five float64 FMAs,
+// every A sample once per CTA of its window (L2).  The tiles reach shared memory through a ring of 1-D TMA
+// bulk copies issued by a producer warp (see the kernel).  xcorr_pick_blocks_kernel adds the partials in
 // a fixed order (deterministic) and scans the candidates.  Sums are float64 (the float32 inputs are
 // exact in float64; the reference's float32 BLAS sums differ from these by rounding only).
 // The general (win, stride) case of the C ABI — more than 4 blocks per window — keeps the direct
@@ -89,266 +90,24 @@ __global__ void __launch_bounds__(kXcThreads) xcorr_dots_kernel(const float *__r
 }
 
 // ---- block form: stride-long blocks of B, nq = win / stride <= 4 of them per candidate ----------------------------------
-constexpr int kBlocksPerCta = 4;   // B blocks whose partial sums one thread keeps (4 × 5 float64 accumulators)
 constexpr int kMaxPieces = 4;      // A blocks per window (win / stride)
 
-// grid (ceil(max_blocks / kBlocksPerCta), n_windows).  part[w][q][m] (q < nq) = <A block q, B block m>,
-// part[w][kMaxPieces][m] = ‖B block m‖²;  na2[w] = ‖wa‖² (from the CTA of blockIdx.x == 0).
-template <int NQ>
-__global__ void __launch_bounds__(kXcThreads) xcorr_blocks_kernel(const float *__restrict__ a, const float *__restrict__ b,
-                                                                   const int64_t *__restrict__ a_pos,
-                                                                   const int64_t *__restrict__ b_lo,
-                                                                   const int32_t *__restrict__ n_cand, int max_blocks,
-                                                                   int win, int stride, double *__restrict__ part,
-                                                                   double *__restrict__ na2) {
-    __shared__ double sh[kXcThreads / 32];
-    const int w = blockIdx.y;
-    const int nc = n_cand[w];
-    if (nc <= 0 && blockIdx.x != 0) return;
-    const int n_blocks = nc > 0 ? nc + NQ - 1 : 0;       // blocks that belong to at least one candidate
-    const int m0 = blockIdx.x * kBlocksPerCta;
-    if (m0 >= n_blocks && blockIdx.x != 0) return;
-    const float *wa = a + a_pos[w];
-    const float *wb = b + b_lo[w] + (int64_t)m0 * stride;
-    const int live = max(0, min(kBlocksPerCta, n_blocks - m0));
-    double d[kBlocksPerCta][NQ], s2[kBlocksPerCta], sa = 0.0;
-#pragma unroll
-    for (int g = 0; g < kBlocksPerCta; ++g) {
-        s2[g] = 0.0;
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) d[g][q] = 0.0;
-    }
-    if (live == kBlocksPerCta) {
-        for (int i = threadIdx.x; i < stride; i += kXcThreads) {
-            double x[NQ], y[kBlocksPerCta];
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) x[q] = (double)__ldg(wa + (int64_t)q * stride + i);
-#pragma unroll
-            for (int g = 0; g < kBlocksPerCta; ++g) y[g] = (double)__ldg(wb + (int64_t)g * stride + i);
-#pragma unroll
-            for (int g = 0; g < kBlocksPerCta; ++g) {
-                s2[g] = fma(y[g], y[g], s2[g]);
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) d[g][q] = fma(x[q], y[g], d[g][q]);
-            }
-            if (blockIdx.x == 0) {
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) sa = fma(x[q], x[q], sa);
-            }
-        }
-    } else {
-        for (int i = threadIdx.x; i < stride; i += kXcThreads) {
-            double x[NQ];
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) x[q] = (double)__ldg(wa + (int64_t)q * stride + i);
-#pragma unroll
-            for (int g = 0; g < kBlocksPerCta; ++g) {
-                if (g < live) {
-                    const double y = (double)__ldg(wb + (int64_t)g * stride + i);
-                    s2[g] = fma(y, y, s2[g]);
-#pragma unroll
-                    for (int q = 0; q < NQ; ++q) d[g][q] = fma(x[q], y, d[g][q]);
-                }
-            }
-            if (blockIdx.x == 0) {
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) sa = fma(x[q], x[q], sa);
-            }
-        }
-    }
-    double *pw = part + (size_t)w * (kMaxPieces + 1) * max_blocks;
-#pragma unroll
-    for (int g = 0; g < kBlocksPerCta; ++g) {
-        if (g < live) {  // CTA-uniform
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-                const double v = block_sum_256(d[g][q], sh);
-                if (threadIdx.x == 0) pw[(size_t)q * max_blocks + m0 + g] = v;
-            }
-            const double v = block_sum_256(s2[g], sh);
-            if (threadIdx.x == 0) pw[(size_t)kMaxPieces * max_blocks + m0 + g] = v;
-        }
-    }
-    if (blockIdx.x == 0) {
-        // the tail samples [NQ·stride, win) of wa belong to ‖wa‖² too
-        for (int i = NQ * stride + threadIdx.x; i < win; i += kXcThreads) {
-            const double x = (double)__ldg(wa + i);
-            sa = fma(x, x, sa);
-        }
-        sa = block_sum_256(sa, sh);
-        if (threadIdx.x == 0) na2[w] = sa;
-    }
-}
-
-// ---- the same block form fed by the TMA engine ------------------------------------------------------------------------
-// The register form above keeps 8 scalar loads per thread in flight — 16 KB per SM at two CTAs of 84 registers — and
-// stalls on them (ncu: long_scoreboard 15.6 per issue, DRAM at 1.1 TB/s).  Here one thread per CTA streams the four A
-// blocks and the CTA's four B blocks through a 3-stage ring of shared-memory tiles with 1-D bulk async copies
-// (cp.async.bulk + mbarrier complete_tx: ~130 KB in flight per SM, independent of occupancy) and the 256 threads only
-// do shared-memory loads and float64 FMAs.  Blocks start at arbitrary sample offsets, bulk copies need 16-byte
-// alignment: a tile is the aligned superset of its chunk (start rounded down, length rounded up to 16 B — the buffers
-// must be readable up to the next 16-byte boundary, as every cudaMalloc'ed allocation is) and is read at an offset.
-constexpr int kXbChunk = 1024;                 // samples of a block per stage
-constexpr int kXbStages = 3;
-constexpr int kXbTileFloats = kXbChunk + 8;    // chunk + alignment slack, multiple of 4
-
-template <int NQ>
-struct XbSmem {
-    float tile[kXbStages][NQ + kBlocksPerCta][kXbTileFloats];
-    uint64_t full[kXbStages];
-};
-
-template <int NQ>
-__global__ void __launch_bounds__(kXcThreads) xcorr_blocks_tma_kernel(const float *__restrict__ a,
-                                                                       const float *__restrict__ b,
-                                                                       const int64_t *__restrict__ a_pos,
-                                                                       const int64_t *__restrict__ b_lo,
-                                                                       const int32_t *__restrict__ n_cand, int max_blocks,
-                                                                       int win, int stride, double *__restrict__ part,
-                                                                       double *__restrict__ na2) {
-    using namespace tc05;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    XbSmem<NQ> &sm = *reinterpret_cast<XbSmem<NQ> *>(smem_raw);
-    __shared__ double sh[kXcThreads / 32];
-    const int w = blockIdx.y;
-    const int nc = n_cand[w];
-    if (nc <= 0 && blockIdx.x != 0) return;
-    const int n_blocks = nc > 0 ? nc + NQ - 1 : 0;
-    const int m0 = blockIdx.x * kBlocksPerCta;
-    if (m0 >= n_blocks && blockIdx.x != 0) return;
-    const float *wa = a + a_pos[w];
-    const float *wb = b + b_lo[w] + (int64_t)m0 * stride;
-    const int live = max(0, min(kBlocksPerCta, n_blocks - m0));
-    const int n_tiles = NQ + live;
-    const int tid = threadIdx.x;
-    // per-tile sample offset inside its aligned superset (the same for every chunk: chunks start at multiples of 1024)
-    int off[NQ + kBlocksPerCta];
-#pragma unroll
-    for (int t = 0; t < NQ + kBlocksPerCta; ++t) {
-        const float *base = t < NQ ? wa + (int64_t)t * stride : wb + (int64_t)(t - NQ) * stride;
-        off[t] = (int)((reinterpret_cast<uintptr_t>(base) & 15u) >> 2);
-    }
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < kXbStages; ++s) mbar_init(&sm.full[s], 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    const int n_chunks = (stride + kXbChunk - 1) / kXbChunk;
-    auto issue = [&](int c) {  // thread 0 only
-        const int st = c % kXbStages;
-        const int i0 = c * kXbChunk;
-        const int len = min(kXbChunk, stride - i0);
-        uint32_t total = 0;
-        for (int t = 0; t < n_tiles; ++t) {
-            const float *base = t < NQ ? wa + (int64_t)t * stride : wb + (int64_t)(t - NQ) * stride;
-            const int o = (int)((reinterpret_cast<uintptr_t>(base) & 15u) >> 2);
-            total += (uint32_t)((o + len + 3) & ~3) * 4u;
-        }
-        mbar_arrive_expect_tx(&sm.full[st], total);
-        for (int t = 0; t < n_tiles; ++t) {
-            const float *base = t < NQ ? wa + (int64_t)t * stride : wb + (int64_t)(t - NQ) * stride;
-            const int o = (int)((reinterpret_cast<uintptr_t>(base) & 15u) >> 2);
-            bulk_g2s(&sm.tile[st][t][0], base + i0 - o, (uint32_t)((o + len + 3) & ~3) * 4u, &sm.full[st]);
-        }
-    };
-    if (tid == 0)
-        for (int c = 0; c < kXbStages - 1 && c < n_chunks; ++c) issue(c);
-
-    double d[kBlocksPerCta][NQ], s2[kBlocksPerCta], sa = 0.0;
-#pragma unroll
-    for (int g = 0; g < kBlocksPerCta; ++g) {
-        s2[g] = 0.0;
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) d[g][q] = 0.0;
-    }
-    for (int c = 0; c < n_chunks; ++c) {
-        // the stage refilled here was consumed in iteration c − 1 (the __syncthreads below orders those reads first)
-        if (tid == 0 && c + kXbStages - 1 < n_chunks) issue(c + kXbStages - 1);
-        const int st = c % kXbStages;
-        mbar_wait_warp(&sm.full[st], (uint32_t)(c / kXbStages) & 1u);
-        const int len = min(kXbChunk, stride - c * kXbChunk);
-        if (live == kBlocksPerCta) {
-#pragma unroll
-            for (int k = 0; k < kXbChunk / kXcThreads; ++k) {
-                const int i = tid + k * kXcThreads;
-                if (i < len) {
-                    double x[NQ], y[kBlocksPerCta];
-#pragma unroll
-                    for (int q = 0; q < NQ; ++q) x[q] = (double)sm.tile[st][q][off[q] + i];
-#pragma unroll
-                    for (int g = 0; g < kBlocksPerCta; ++g) y[g] = (double)sm.tile[st][NQ + g][off[NQ + g] + i];
-#pragma unroll
-                    for (int g = 0; g < kBlocksPerCta; ++g) {
-                        s2[g] = fma(y[g], y[g], s2[g]);
-#pragma unroll
-                        for (int q = 0; q < NQ; ++q) d[g][q] = fma(x[q], y[g], d[g][q]);
-                    }
-                    if (blockIdx.x == 0) {
-#pragma unroll
-                        for (int q = 0; q < NQ; ++q) sa = fma(x[q], x[q], sa);
-                    }
-                }
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < kXbChunk / kXcThreads; ++k) {
-                const int i = tid + k * kXcThreads;
-                if (i < len) {
-                    double x[NQ];
-#pragma unroll
-                    for (int q = 0; q < NQ; ++q) x[q] = (double)sm.tile[st][q][off[q] + i];
-#pragma unroll
-                    for (int g = 0; g < kBlocksPerCta; ++g) {
-                        if (g < live) {
-                            const double y = (double)sm.tile[st][NQ + g][off[NQ + g] + i];
-                            s2[g] = fma(y, y, s2[g]);
-#pragma unroll
-                            for (int q = 0; q < NQ; ++q) d[g][q] = fma(x[q], y, d[g][q]);
-                        }
-                    }
-                    if (blockIdx.x == 0) {
-#pragma unroll
-                        for (int q = 0; q < NQ; ++q) sa = fma(x[q], x[q], sa);
-                    }
-                }
-            }
-        }
-        __syncthreads();
-    }
-    double *pw = part + (size_t)w * (kMaxPieces + 1) * max_blocks;
-#pragma unroll
-    for (int g = 0; g < kBlocksPerCta; ++g) {
-        if (g < live) {  // CTA-uniform
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-                const double v = block_sum_256(d[g][q], sh);
-                if (tid == 0) pw[(size_t)q * max_blocks + m0 + g] = v;
-            }
-            const double v = block_sum_256(s2[g], sh);
-            if (tid == 0) pw[(size_t)kMaxPieces * max_blocks + m0 + g] = v;
-        }
-    }
-    if (blockIdx.x == 0) {
-        for (int i = NQ * stride + tid; i < win; i += kXcThreads) {
-            const double x = (double)__ldg(wa + i);
-            sa = fma(x, x, sa);
-        }
-        sa = block_sum_256(sa, sh);
-        if (tid == 0) na2[w] = sa;
-    }
-}
-
-// ---- ring form (the default): the same tiles through a ring with full / empty mbarriers and a producer warp ------------
-// ncu on the kernel above (profiles/r2f_ncu_summary.md): FP64 pipe 20 %, XU (float → double conversions) 28 %, and a third
-// of all stall samples sit behind the per-chunk __syncthreads: warp 0's single lane walks the eight tiles twice (byte
-// count, then the copies — a serial ~1000-cycle path, longer than the chunk's arithmetic), and everybody waits for it.
-// Here nothing is CTA-wide inside the loop: the last warp only produces (lane t owns tile t: eight lanes issue the eight
-// bulk copies of a stage in parallel, from pointers computed once), the other warps only consume (wait full → shared
-// loads + float64 FMAs → one arrive per warp on the stage's empty barrier).  A first version with 512-sample chunks
-// (2 KB copies, six stages, two CTAs per SM) ran at 1.5 TB/s against 2.6 TB/s for the 4 KB copies above: the SM's copy
-// engine spends a fixed ~200 cycles per bulk copy at these 16-byte-aligned addresses, so bytes per copy set the rate —
-// hence 2048-sample chunks (8 KB copies), three stages (197 KB), one CTA of 16 consumer warps per SM.
+// ---- ring form: the tiles of a CTA stream through a ring with full / empty mbarriers and a producer warp ---------------
+// History of this kernel on B200 (config 4, 16 pairs, algorithmic bytes per second; profiles/README.md has the files):
+//   one CTA per (window, candidate), scalar loads (round 1)                                             0.35 TB/s
+//   block form, register loads (8 in flight per thread: long-scoreboard bound)                          1.1
+//   block form, 3-stage TMA ring, one lane computes byte counts and issues all copies, __syncthreads    2.6
+//     (ncu r2f: a third of all stall samples behind that barrier — the issuing lane's serial path)
+//   producer warp (lane t owns tile t), full / empty mbarriers, 512-sample chunks = 2 KB copies         1.5
+//     (the SM's copy engine has a fixed cost per bulk copy: 2 KB copies sustain 16 B/clk/SM, 4 KB 25 —
+//      profiles/r2k_tma_bulk_copy_bandwidth.log)
+//   same with 8 KB copies, 4 B blocks per CTA                                                           2.6
+//   8 B blocks per CTA (the A re-reads drop from 1/2 to 1/3 of the bytes), 4 KB copies, 4 stages        2.7
+//   + the CTA's 41 sums reduced through the idle ring memory with two barriers instead of 123           3.0
+// Not kept: A blocks through registers with only B in the ring (2.45), two CTAs per SM at 112 registers (1.95).
+// Nothing is CTA-wide inside the loop: the last warp only produces (eight..twelve lanes issue the bulk copies of a stage
+// in parallel, from pointers computed once), the other warps only consume (wait full → shared loads + float64 FMAs → one
+// arrive per warp on the stage's empty barrier).
 // G = B blocks per CTA.  The A blocks are re-read by every CTA of a window, so the bytes a CTA pulls through the copy
 // engine are (NQ + G) / G times its algorithmic share: 2x at G = 4, 1.5x at G = 8 (40 float64 accumulators per thread).
 template <int NQ, int G, int CHUNK, int STAGES, int CONSUMERS>
@@ -357,25 +116,8 @@ struct XrSmem {
     uint64_t full[STAGES], empty[STAGES];
 };
 
-// block sum over the consumer threads (named barrier 1: the producer warp is not part of it)
-template <int CONSUMERS>
-__device__ __forceinline__ double consumer_sum(double v, double *sh) {
-    v = warp_sum(v);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
-    asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");
-    double s = 0.0;
-    if (threadIdx.x == 0) {
-        for (int w = 0; w < CONSUMERS / 32; ++w) s += sh[w];
-        sh[0] = s;
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");
-    s = sh[0];
-    asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");
-    return s;
-}
-
-template <int NQ, int G, int CHUNK, int STAGES, int CONSUMERS, int MINB = 1>
-__global__ void __launch_bounds__(CONSUMERS + 32, MINB) xcorr_blocks_ring_kernel(const float *__restrict__ a,
+template <int NQ, int G, int CHUNK, int STAGES, int CONSUMERS>
+__global__ void __launch_bounds__(CONSUMERS + 32, 1) xcorr_blocks_ring_kernel(const float *__restrict__ a,
                                                                        const float *__restrict__ b,
                                                                        const int64_t *__restrict__ a_pos,
                                                                        const int64_t *__restrict__ b_lo,
@@ -385,7 +127,6 @@ __global__ void __launch_bounds__(CONSUMERS + 32, MINB) xcorr_blocks_ring_kernel
     using namespace tc05;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     XrSmem<NQ, G, CHUNK, STAGES, CONSUMERS> &sm = *reinterpret_cast<XrSmem<NQ, G, CHUNK, STAGES, CONSUMERS> *>(smem_raw);
-    __shared__ double sh[CONSUMERS / 32];
     const int w = blockIdx.y;
     const int nc = n_cand[w];
     if (nc <= 0 && blockIdx.x != 0) return;
@@ -530,156 +271,6 @@ __global__ void __launch_bounds__(CONSUMERS + 32, MINB) xcorr_blocks_ring_kernel
                 if (g < live) pw[(size_t)(q == NQ ? kMaxPieces : q) * max_blocks + m0 + g] = acc;
             }
         }
-    }
-}
-
-// ---- ring form with the A blocks in registers (experiment, NCFA_XCORR_IMPL=areg) ----------------------------------------
-// ncu on the ring kernel above (profiles/r2i: 4 or 8 B blocks per CTA, 2 KB / 4 KB / 8 KB copies, 3-6 stages, one or two
-// CTAs per SM) always lands on the same ~18 B/clk of bulk-copy traffic per SM with the consumers waiting on the full
-// barriers, i.e. the copy engine of an SM sustains only so many bytes in flight; what counts is how many of those bytes
-// are algorithmic.  The A blocks of a window are re-read by each of its CTAs and are L1/L2 resident, so here they do not
-// go through the copy engine at all: a consumer thread loads the A samples of its own indices straight into registers
-// (coalesced 4-byte loads, issued one chunk ahead), and the ring carries only the CTA's eight B blocks — every byte the
-// copy engine moves is read from HBM exactly once.
-template <int G, int CHUNK, int STAGES>
-struct XaSmem {
-    float tile[STAGES][G][CHUNK + 8];
-    uint64_t full[STAGES], empty[STAGES];
-};
-
-template <int NQ, int G, int CHUNK, int STAGES, int CONSUMERS>
-__global__ void __launch_bounds__(CONSUMERS + 32, 1) xcorr_blocks_areg_kernel(const float *__restrict__ a,
-                                                                              const float *__restrict__ b,
-                                                                              const int64_t *__restrict__ a_pos,
-                                                                              const int64_t *__restrict__ b_lo,
-                                                                              const int32_t *__restrict__ n_cand,
-                                                                              int max_blocks, int win, int stride,
-                                                                              double *__restrict__ part,
-                                                                              double *__restrict__ na2) {
-    using namespace tc05;
-    constexpr int KPER = CHUNK / CONSUMERS;  // sample indices per thread per chunk
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    XaSmem<G, CHUNK, STAGES> &sm = *reinterpret_cast<XaSmem<G, CHUNK, STAGES> *>(smem_raw);
-    __shared__ double sh[CONSUMERS / 32];
-    const int w = blockIdx.y;
-    const int nc = n_cand[w];
-    if (nc <= 0 && blockIdx.x != 0) return;
-    const int n_blocks = nc > 0 ? nc + NQ - 1 : 0;
-    const int m0 = blockIdx.x * G;
-    if (m0 >= n_blocks && blockIdx.x != 0) return;
-    const float *wa = a + a_pos[w];
-    const float *wb = b + b_lo[w] + (int64_t)m0 * stride;
-    const int live = max(0, min(G, n_blocks - m0));
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&sm.full[s], 1);
-            mbar_init(&sm.empty[s], CONSUMERS / 32);
-        }
-        fence_mbar_init();
-    }
-    __syncthreads();
-    const int n_chunks = live > 0 ? (stride + CHUNK - 1) / CHUNK : 0;
-
-    if (warp == CONSUMERS / 32) {
-        // ===================== producer warp: lane g streams B block m0 + g =====================
-        const float *base = wb + (int64_t)lane * stride;
-        const int o = (int)((reinterpret_cast<uintptr_t>(base) & 15u) >> 2);   // offset inside the 16-byte aligned superset
-        for (int c = 0; c < n_chunks; ++c) {
-            const int st = c % STAGES;
-            if (c >= STAGES) mbar_wait_warp(&sm.empty[st], (uint32_t)((c / STAGES - 1) & 1), 20);
-            const int i0 = c * CHUNK;
-            const int len = min(CHUNK, stride - i0);
-            const uint32_t bytes = lane < live ? (uint32_t)((o + len + 3) & ~3) * 4u : 0u;
-            uint32_t total = bytes;
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
-            if (lane == 0) mbar_arrive_expect_tx(&sm.full[st], total);
-            __syncwarp();
-            if (lane < live) bulk_g2s(&sm.tile[st][lane][0], base + i0 - o, bytes, &sm.full[st]);
-        }
-        return;
-    }
-
-    // ===================== consumer warps =====================
-    int off[G];
-#pragma unroll
-    for (int g = 0; g < G; ++g) off[g] = (int)((reinterpret_cast<uintptr_t>(wb + (int64_t)g * stride) & 15u) >> 2);
-    double d[G][NQ], s2[G], sa = 0.0;
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-        s2[g] = 0.0;
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) d[g][q] = 0.0;
-    }
-    float xn[KPER][NQ];  // A samples of the NEXT chunk (0 beyond the block's end: they then add nothing)
-    auto load_a = [&](int c) {
-#pragma unroll
-        for (int k = 0; k < KPER; ++k) {
-            const int i = c * CHUNK + tid + k * CONSUMERS;
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) xn[k][q] = (c < n_chunks && i < stride) ? __ldg(wa + (int64_t)q * stride + i) : 0.0f;
-        }
-    };
-    load_a(0);
-    for (int c = 0; c < n_chunks; ++c) {
-        const int st = c % STAGES;
-        float xc[KPER][NQ];
-#pragma unroll
-        for (int k = 0; k < KPER; ++k)
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) xc[k][q] = xn[k][q];
-        load_a(c + 1);  // in flight while this chunk is consumed
-        mbar_wait_warp(&sm.full[st], (uint32_t)(c / STAGES) & 1u);
-        const int len = min(CHUNK, stride - c * CHUNK);
-#pragma unroll
-        for (int k = 0; k < KPER; ++k) {
-            const int i = tid + k * CONSUMERS;
-            if (i < len) {
-                double x[NQ];
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) x[q] = (double)xc[k][q];
-#pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    if (g < live) {  // CTA-uniform
-                        const double y = (double)sm.tile[st][g][off[g] + i];
-                        s2[g] = fma(y, y, s2[g]);
-#pragma unroll
-                        for (int q = 0; q < NQ; ++q) d[g][q] = fma(x[q], y, d[g][q]);
-                    }
-                }
-                if (blockIdx.x == 0) {
-#pragma unroll
-                    for (int q = 0; q < NQ; ++q) sa = fma(x[q], x[q], sa);
-                }
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.empty[st]);   // this warp is done reading the stage
-    }
-    double *pw = part + (size_t)w * (kMaxPieces + 1) * max_blocks;
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-        if (g < live) {  // CTA-uniform
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-                const double v = consumer_sum<CONSUMERS>(d[g][q], sh);
-                if (tid == 0) pw[(size_t)q * max_blocks + m0 + g] = v;
-            }
-            const double v = consumer_sum<CONSUMERS>(s2[g], sh);
-            if (tid == 0) pw[(size_t)kMaxPieces * max_blocks + m0 + g] = v;
-        }
-    }
-    if (blockIdx.x == 0) {
-        // ‖wa‖²: the block part was accumulated above when the CTA had B blocks; otherwise (no candidate) sum it here
-        const int from = live > 0 ? NQ * stride : 0;
-        for (int i = from + tid; i < win; i += CONSUMERS) {
-            const double x = (double)__ldg(wa + i);
-            sa = fma(x, x, sa);
-        }
-        sa = consumer_sum<CONSUMERS>(sa, sh);
-        if (tid == 0) na2[w] = sa;
     }
 }
 
@@ -917,43 +508,11 @@ __global__ void __launch_bounds__(kXcThreads) align_pick_kernel(const double *__
     }
 }
 
-// NCFA_XCORR_IMPL=regs: the block form with plain register loads instead of the TMA-fed ring (cross-check / before-after)
-static bool xcorr_use_regs() {
-    static const bool v = [] {
-        const char *e = getenv("NCFA_XCORR_IMPL");
-        return e && strcmp(e, "regs") == 0;
-    }();
-    return v;
-}
-// NCFA_XCORR_IMPL=tma3: the 3-stage TMA form with a __syncthreads per chunk (before/after of the ring form)
-static bool xcorr_use_tma3() {
-    static const bool v = [] {
-        const char *e = getenv("NCFA_XCORR_IMPL");
-        return e && strcmp(e, "tma3") == 0;
-    }();
-    return v;
-}
-// NCFA_XCORR_IMPL=ring4: the ring form with four B blocks per CTA (before/after of the eight-block default)
+// NCFA_XCORR_IMPL=ring4: four B blocks per CTA, 8 KB copies, 16 consumer warps (before/after of the eight-block default)
 static bool xcorr_g4() {
     static const bool v = [] {
         const char *e = getenv("NCFA_XCORR_IMPL");
         return e && strcmp(e, "ring4") == 0;
-    }();
-    return v;
-}
-// NCFA_XCORR_IMPL=x2: eight B blocks per CTA, 512-sample chunks, two CTAs per SM (register-capped at 112)
-static bool xcorr_x2() {
-    static const bool v = [] {
-        const char *e = getenv("NCFA_XCORR_IMPL");
-        return e && strcmp(e, "x2") == 0;
-    }();
-    return v;
-}
-// NCFA_XCORR_IMPL=areg: the A blocks through registers, only the B blocks in the ring (measured slower: 2.45 vs 2.7 TB/s)
-static bool xcorr_areg() {
-    static const bool v = [] {
-        const char *e = getenv("NCFA_XCORR_IMPL");
-        return e && strcmp(e, "areg") == 0;
     }();
     return v;
 }
@@ -997,40 +556,18 @@ extern "C" int ncfa_xcorr_search_batched(const float *d_a, const float *d_b, con
         const int max_blocks = max_cand + kMaxPieces - 1;
         double *part = (double *)wp;
         double *na2b = (double *)(wp + align_up((size_t)n_windows * (kMaxPieces + 1) * max_blocks * 8, 256));
-        dim3 g((max_cand + nq - 1 + kBlocksPerCta - 1) / kBlocksPerCta, n_windows);
         {
             ProfScope _p("xcorr_blocks_kernel", st);
-            if (xcorr_use_regs()) {
-                switch (nq) {
-                    case 1: xcorr_blocks_kernel<1><<<g, kXcThreads, 0, st>>>(d_a, d_b, d_a_pos, d_b_lo, d_n_cand, max_blocks, win, stride, part, na2b); break;
-                    case 2: xcorr_blocks_kernel<2><<<g, kXcThreads, 0, st>>>(d_a, d_b, d_a_pos, d_b_lo, d_n_cand, max_blocks, win, stride, part, na2b); break;
-                    case 3: xcorr_blocks_kernel<3><<<g, kXcThreads, 0, st>>>(d_a, d_b, d_a_pos, d_b_lo, d_n_cand, max_blocks, win, stride, part, na2b); break;
-                    default: xcorr_blocks_kernel<4><<<g, kXcThreads, 0, st>>>(d_a, d_b, d_a_pos, d_b_lo, d_n_cand, max_blocks, win, stride, part, na2b); break;
-                }
-            } else if (!xcorr_use_tma3()) {
-                int rc = 0;
+            int rc = 0;
 #define NCFA_XR_LAUNCH(NQ_)                                                                                             \
     do {                                                                                                                \
-        if (xcorr_x2()) {                                                                                               \
-            using Sm = XrSmem<NQ_, 8, 512, 4, 256>;                                                                     \
-            auto kfn = xcorr_blocks_ring_kernel<NQ_, 8, 512, 4, 256, 2>;                                                \
-            if ((rc = ensure_dynamic_smem((const void *)kfn, sizeof(Sm)))) return rc;                                   \
-            dim3 g8((max_cand + nq - 1 + 7) / 8, n_windows);                                                            \
-            kfn<<<g8, 256 + 32, sizeof(Sm), st>>>(d_a, d_b, d_a_pos, d_b_lo, d_n_cand, max_blocks, win, stride, part,   \
-                                                  na2b);                                                                \
-        } else if (xcorr_areg()) {                                                                                      \
-            using Sm = XaSmem<8, 1024, 6>;                                                                              \
-            auto kfn = xcorr_blocks_areg_kernel<NQ_, 8, 1024, 6, 256>;                                                  \
-            if ((rc = ensure_dynamic_smem((const void *)kfn, sizeof(Sm)))) return rc;                                   \
-            dim3 g8((max_cand + nq - 1 + 7) / 8, n_windows);                                                            \
-            kfn<<<g8, 256 + 32, sizeof(Sm), st>>>(d_a, d_b, d_a_pos, d_b_lo, d_n_cand, max_blocks, win, stride, part,   \
-                                                  na2b);                                                                \
-        } else if (xcorr_g4()) {                                                                                        \
+        if (xcorr_g4()) {                                                                                               \
             using Sm = XrSmem<NQ_, 4, 2048, 3, 512>;                                                                    \
             auto kfn = xcorr_blocks_ring_kernel<NQ_, 4, 2048, 3, 512>;                                                  \
             if ((rc = ensure_dynamic_smem((const void *)kfn, sizeof(Sm)))) return rc;                                   \
-            kfn<<<g, 512 + 32, sizeof(Sm), st>>>(d_a, d_b, d_a_pos, d_b_lo, d_n_cand, max_blocks, win, stride, part,    \
-                                                 na2b);                                                                 \
+            dim3 g4((max_cand + nq - 1 + 3) / 4, n_windows);                                                            \
+            kfn<<<g4, 512 + 32, sizeof(Sm), st>>>(d_a, d_b, d_a_pos, d_b_lo, d_n_cand, max_blocks, win, stride, part,   \
+                                                  na2b);                                                                \
         } else {                                                                                                        \
             using Sm = XrSmem<NQ_, 8, 1024, 4, 256>;                                                                    \
             auto kfn = xcorr_blocks_ring_kernel<NQ_, 8, 1024, 4, 256>;                                                  \
@@ -1040,29 +577,13 @@ extern "C" int ncfa_xcorr_search_batched(const float *d_a, const float *d_b, con
                                                   na2b);                                                                \
         }                                                                                                               \
     } while (0)
-                switch (nq) {
-                    case 1: NCFA_XR_LAUNCH(1); break;
-                    case 2: NCFA_XR_LAUNCH(2); break;
-                    case 3: NCFA_XR_LAUNCH(3); break;
-                    default: NCFA_XR_LAUNCH(4); break;
-                }
-#undef NCFA_XR_LAUNCH
-            } else {
-                int rc = 0;
-#define NCFA_XB_LAUNCH(NQ_)                                                                                             \
-    do {                                                                                                                \
-        if ((rc = ensure_dynamic_smem((const void *)xcorr_blocks_tma_kernel<NQ_>, sizeof(XbSmem<NQ_>)))) return rc;     \
-        xcorr_blocks_tma_kernel<NQ_><<<g, kXcThreads, sizeof(XbSmem<NQ_>), st>>>(d_a, d_b, d_a_pos, d_b_lo, d_n_cand,    \
-                                                                                 max_blocks, win, stride, part, na2b);  \
-    } while (0)
-                switch (nq) {
-                    case 1: NCFA_XB_LAUNCH(1); break;
-                    case 2: NCFA_XB_LAUNCH(2); break;
-                    case 3: NCFA_XB_LAUNCH(3); break;
-                    default: NCFA_XB_LAUNCH(4); break;
-                }
-#undef NCFA_XB_LAUNCH
+            switch (nq) {
+                case 1: NCFA_XR_LAUNCH(1); break;
+                case 2: NCFA_XR_LAUNCH(2); break;
+                case 3: NCFA_XR_LAUNCH(3); break;
+                default: NCFA_XR_LAUNCH(4); break;
             }
+#undef NCFA_XR_LAUNCH
         }
         NCFA_LAUNCH_OK("xcorr_blocks_kernel");
         {
