@@ -9,6 +9,7 @@ from __future__ import annotations
 import math
 import os
 import threading
+import weakref
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -202,6 +203,10 @@ class Engine:
         if n_seg == 0:
             return lag[:0]
         W = int(math.floor(8.0 * sr / hop))
+        if not 4 <= W <= 5000:
+            # the tempogram kernels keep one 8-second window of the envelope per CTA in shared memory
+            raise ValueError(f"unsupported sr / hop for the tempogram: its 8 s window is {W} onset frames at sr={sr}, "
+                             f"hop={hop}; supported: 4..5000 frames (sr/hop <= 625, e.g. sr <= 40000 Hz at hop 64)")
         with torch.cuda.device(self.device):
             st = self._stream()
             for s in range(0, n_seg, MAX_SEGS_PER_CALL):
@@ -492,24 +497,39 @@ class Engine:
         return hl, [hb[i, : hn[i]].copy() for i in range(len(arrays))]
 
 
-_ENGINES: dict = {}
+_ENGINES: dict = {}          # (device index, thread ident) -> (Engine, weakref to the owning thread)
 _ENG_LOCK = threading.Lock()
+_RETIRED_LAUNCHES = 0        # launches of engines whose threads have ended (total_launches stays monotonic)
+
+
+def _drop_dead_engines() -> None:
+    """Engines belong to host threads (each pins a parameter ring and owns device workspaces).  A thread that has ended
+    must not keep them alive — nor hand them, through a recycled thread ident, to an unrelated new thread."""
+    global _RETIRED_LAUNCHES
+    for key in [k for k, (_, ref) in _ENGINES.items() if ref() is None or not ref().is_alive()]:
+        eng, _ = _ENGINES.pop(key)
+        _RETIRED_LAUNCHES += eng.launches
 
 
 def get_engine(device=None) -> Engine:
     """The calling thread's engine for `device` (workspaces are per engine, so concurrent host threads — each on its own
-    CUDA stream — never share scratch buffers)."""
+    CUDA stream — never share scratch buffers).  Engines of threads that have ended are released on the next call."""
     if not torch.cuda.is_available():
         raise _native.NcfaError("nightcore_analyzer needs a CUDA device (sm_100a); there is no CPU fallback")
     idx = torch.cuda.current_device() if device is None else torch.device(device).index or 0
-    key = (idx, threading.get_ident())
+    me = threading.current_thread()
+    key = (idx, me.ident)
     with _ENG_LOCK:
-        if key not in _ENGINES:
-            _ENGINES[key] = Engine(torch.device("cuda", idx))
-        return _ENGINES[key]
+        hit = _ENGINES.get(key)
+        if hit is not None and hit[1]() is me:
+            return hit[0]
+        _drop_dead_engines()
+        eng = Engine(torch.device("cuda", idx))
+        _ENGINES[key] = (eng, weakref.ref(me))
+        return eng
 
 
 def total_launches() -> int:
     """Kernels launched by every engine of this process (bench.py's gpu_launches)."""
     with _ENG_LOCK:
-        return sum(e.launches for e in _ENGINES.values())
+        return _RETIRED_LAUNCHES + sum(e.launches for e, _ in _ENGINES.values())

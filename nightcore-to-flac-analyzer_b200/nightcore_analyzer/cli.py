@@ -76,12 +76,18 @@ def _run_batch(args, silence_strip_db) -> int:
             print(f"ERROR: malformed manifest line: {line!r}", file=sys.stderr)
             return 2
         names.append(parts)
-    for nc_path, src_path in names:
-        nc, sr = load_audio(nc_path)
-        src, _ = load_audio(src_path, sr=sr)
+    load_errors = {}
+    for k, (nc_path, src_path) in enumerate(names):
+        try:                                  # an unreadable entry becomes that entry's "error", not a traceback
+            nc, sr = load_audio(nc_path)
+            src, _ = load_audio(src_path, sr=sr)
+        except Exception as exc:  # noqa: BLE001
+            load_errors[k] = exc
+            continue
         pairs.append((nc, src))
-    results = pipeline.run_batch(pairs, window_sec=args.window, hop_sec=args.hop, energy_gate_db=args.energy_gate,
-                                 silence_strip_db=silence_strip_db)
+    analysed = iter(pipeline.run_batch(pairs, window_sec=args.window, hop_sec=args.hop, energy_gate_db=args.energy_gate,
+                                       silence_strip_db=silence_strip_db) if pairs else [])
+    results = [load_errors[k] if k in load_errors else next(analysed) for k in range(len(names))]
     out = []
     for (nc_path, src_path), res in zip(names, results):
         entry = {"nightcore": nc_path, "source": src_path}
@@ -99,6 +105,9 @@ def main(argv: Optional[List[str]] = None) -> int:
     if args.batch:
         if not Path(args.batch).exists():
             problems.append(f"Manifest file not found: {args.batch}")
+        if args.src_trim_sec != 0.0 or args.auto_align:
+            # run_batch has no per-pair intro trim / alignment stage (pipeline.py:91-139 runs only in the single-pair path)
+            problems.append("--src-trim-sec / --auto-align apply to a single pair and cannot be combined with --batch")
     else:
         if not args.nightcore or not args.source:
             problems.append("--nightcore and --source are required (or --batch MANIFEST)")

@@ -63,6 +63,22 @@ def test_cli_argument_validation(tmp_path, capsys):
     assert "ERROR: Nightcore file not found:" in err and "ERROR: Source file not found:" in err
     assert "ERROR: --hop must be less than --window for overlapping windows" in err
     assert cli.main(["--batch", str(tmp_path / "nope.txt")]) == 2
+    # single-pair stages cannot be combined with a manifest (run_batch has no intro trim / alignment stage)
+    (tmp_path / "m.txt").write_text("a.npy,b.npy\n")
+    capsys.readouterr()
+    assert cli.main(["--batch", str(tmp_path / "m.txt"), "--auto-align"]) == 2
+    assert "cannot be combined with --batch" in capsys.readouterr().err
+    assert cli.main(["--batch", str(tmp_path / "m.txt"), "--src-trim-sec", "1.5"]) == 2
+
+
+def test_cli_batch_reports_unreadable_entries_per_entry(tmp_path):
+    """A manifest whose files cannot be read yields one "error" entry per line and exit code 1 — no traceback, and no
+    device work (nothing is left to analyse)."""
+    from nightcore_analyzer import cli
+    (tmp_path / "m.txt").write_text(f"{tmp_path/'no_nc.npy'},{tmp_path/'no_src.npy'}\n")
+    rc = cli.main(["--batch", str(tmp_path / "m.txt"), "-o", str(tmp_path / "b.json"), "-q"])
+    rows = json.loads((tmp_path / "b.json").read_text())
+    assert rc == 1 and len(rows) == 1 and "error" in rows[0] and rows[0]["nightcore"].endswith("no_nc.npy")
 
 
 @pytest.mark.gpu

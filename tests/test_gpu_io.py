@@ -53,3 +53,30 @@ def test_rms_frames(engine):
     assert got.shape == want.shape
     # oracle: float32 mean (numpy pairwise); device: float64 accumulation rounded once — a few float32 ulps
     assert np.max(np.abs(got - want)) <= 2e-6 * float(np.max(want)) + 1e-12
+
+
+def test_engines_of_ended_threads_are_released(engine):
+    """An engine (pinned parameter ring + device workspaces) belongs to the host thread that created it and goes away
+    with it; the launch counter stays monotonic."""
+    import threading
+    from nightcore_analyzer import _engine
+    before = _engine.total_launches()
+    seen = {}
+
+    def work():
+        eng = _engine.get_engine()
+        seen["id"] = id(eng)
+        eng.window_energy_dev(eng.pack([np.ones(4096, np.float32)])[0], eng.to_dev(np.array([0], np.int64)),
+                              eng.to_dev(np.array([4096], np.int32)))
+        seen["launches"] = eng.launches
+
+    t = threading.Thread(target=work)
+    t.start()
+    t.join()
+    assert seen["launches"] > 0
+    mine = _engine.get_engine()                 # same thread as the fixture: the cached engine, not a new one
+    assert mine is engine
+    with _engine._ENG_LOCK:
+        _engine._drop_dead_engines()
+        assert all(id(e) != seen["id"] for e, _ in _engine._ENGINES.values())
+    assert _engine.total_launches() >= before + seen["launches"]
