@@ -217,6 +217,9 @@ def run_gpu(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local_rank)
+    # torchrun exports OMP_NUM_THREADS=1 to every rank, which makes the pageable → pinned staging copy of
+    # run_batch(list of numpy arrays) single-threaded; give every rank its share of the host cores instead
+    torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(1, world)))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))

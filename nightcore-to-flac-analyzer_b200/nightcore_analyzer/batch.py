@@ -329,6 +329,13 @@ def _first_job_pairs(n_pairs: int, sub: int) -> int:
     return 8   # measured on B200, 1000 pairs (profiles/r2l): first = 8 → 1107 pairs/s end to end, 24 → 913, 48 → 891, 83 → 890
 
 
+def _job_growth() -> float:
+    """Growth factor of the streamed job sizes (NCFA_E2E_GROWTH overrides; experiments)."""
+    import os
+    env = os.environ.get("NCFA_E2E_GROWTH")
+    return float(env) if env else 1.5
+
+
 # ------------------------------------------------------------------------------------------------ the batch scheduler
 # One stager thread walks the jobs (consecutive, disjoint slices of the batch) in order: it lays a slice out in pinned
 # memory when the caller's arrays are pageable, queues its host→HBM copy on a copy stream into one of `workers + 1`
@@ -397,7 +404,8 @@ def analyse_batch(source, sr: int = SAMPLE_RATE, *, sub_batch: int = SUB_BATCH_P
     if P == 0:
         return []
     if sizes is None:
-        sizes = [P] if P <= INLINE_PAIRS else plan_subbatches(P, sub_batch, workers, first=_first_job_pairs(P, sub_batch))
+        sizes = [P] if P <= INLINE_PAIRS else plan_subbatches(P, sub_batch, workers, first=_first_job_pairs(P, sub_batch),
+                                                              growth=_job_growth())
     sizes = [int(k) for k in sizes]
     if any(k <= 0 for k in sizes) or sum(sizes) != P:
         raise ValueError(f"sub-batch sizes {sizes} do not cover the {P} pairs of the batch exactly once")
