@@ -240,7 +240,12 @@ def run_gpu(args):
     # the rank's pairs in pinned host memory (the contract's e2e starts here) and resident in HBM (`value`)
     pinned = nbatch.pin_pairs(pairs_np, SR)
     n_mine = len(my_ids)
-    sub = max(1, min(args.sub_batch, max(16, -(-n_mine // 4)))) if n_mine else 1     # at least ~4 sub-batches per rank
+    if args.sub_batch > 0:
+        sub = args.sub_batch                                                        # explicit: as given
+    else:
+        # default 125 pairs per job whatever the share: small jobs inflate the kernel time (latency-bound kernels: 87 ms of
+        # kernels for 125 pairs in one job, 116-126 ms in five), measured profiles/r2q_*: one job 1287 pairs/s, five jobs 1081
+        sub = 125
     sizes = nbatch.stagger_sizes(n_mine, sub, args.workers)          # first job short: the workers run out of phase
     starts = [sum(sizes[:j]) for j in range(len(sizes))]
     resident = [nbatch.upload(pinned, k, start_pair=s) for s, k in zip(starts, sizes)]
@@ -352,6 +357,8 @@ def run_gpu(args):
             "e2e": {"value": windows_e / (ms_e2e / 1e3), "unit": "windows/s", "ms_per_step": ms_e2e,
                     "pairs_per_sec": pps_e, "audio_sec_per_sec": audio_seconds(pps_e, args.pair_sec),
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "h2d_copy_gbs_rank0": round(float(stats_e.get("h2d_copy_gbs", 0.0)), 2),
+                    "h2d_copy_ms_rank0": round(float(stats_e.get("h2d_copy_ms", 0.0)), 1),
                     "api": "nightcore_analyzer.run_batch(PinnedBatch) — pinned host memory in, AnalysisResult objects out"},
             "gather_identical": gather_identical,
             "gpu_launches": int(launches),
@@ -532,7 +539,7 @@ def main():
     ap.add_argument("--config", type=int, default=5, choices=[2, 3, 4, 5], help="BASELINE config (5 = the contract line)")
     ap.add_argument("--pairs", type=int, default=1000, help="total track pairs per step (all ranks)")
     ap.add_argument("--pair-sec", type=float, default=PAIR_SEC)
-    ap.add_argument("--sub-batch", type=int, default=125, help="pairs analysed per device pass (per rank)")
+    ap.add_argument("--sub-batch", type=int, default=0, help="pairs analysed per device pass (per rank); 0 = 125")
     ap.add_argument("--workers", type=int, default=2, help="host threads / CUDA streams the sub-batches are dealt to")
     ap.add_argument("--no-pitch", action="store_true")
     ap.add_argument("--no-ibi", action="store_true")

@@ -300,16 +300,20 @@ def analyse_staged(batch: StagedBatch, *, window_sec: float = WINDOW_SEC, hop_se
 def plan_subbatches(n_pairs: int, sub: int, workers: int = 2, first: int = 8, growth: float = 1.5) -> List[int]:
     """Sub-batch sizes for ``n_pairs`` pairs, at most ``sub`` each.  A job can start only when its upload is complete,
     and the upload of the next job runs while the current ones compute; the copy engine moves a pair about twice
-    as fast as the kernels analyse one, so sizes grow geometrically (``first``, x ``growth`` < 2) until they reach
+    as fast as the kernels analyse one, so sizes grow geometrically (``first``, x ``growth``) until they reach
     ``sub``: every upload hides behind the compute of the jobs before it and only the first few pairs' copy is
-    exposed.  The rest is split evenly (no short tail job)."""
+    exposed.  The rest is split evenly (no short tail job); a remainder smaller than the job before it is folded into
+    that job (a batch of 125 pairs becomes 8, 12, 18, 27, 60 — not one unstreamed pass)."""
     sizes: List[int] = []
     left = int(n_pairs)
     sub = max(1, int(sub))
     s = float(max(1, first))
-    while int(s) < sub and left - int(s) >= sub:
-        sizes.append(int(s))
-        left -= int(s)
+    while left > 0 and int(s) < sub:
+        k = min(int(s), left)
+        if left - k < k:
+            k = left
+        sizes.append(k)
+        left -= k
         s *= growth
     if left > 0:
         k = -(-left // sub)
@@ -439,6 +443,7 @@ def analyse_batch(source, sr: int = SAMPLE_RATE, *, sub_batch: int = SUB_BATCH_P
         copy_stream.wait_stream(main)
         out: list = [None] * len(sizes)
         errors: list = []
+        copy_events: list = []   # (start, end, bytes) of every host→HBM copy, on the copy stream's clock
 
         def stager():
             try:
@@ -460,9 +465,12 @@ def analyse_batch(source, sr: int = SAMPLE_RATE, *, sub_batch: int = SUB_BATCH_P
                         src = sl.pinned[:total]
                     with torch.cuda.stream(copy_stream):
                         copy_stream.wait_event(sl.free)
+                        ev0 = torch.cuda.Event(enable_timing=True)
+                        ev0.record(copy_stream)
                         sl.dev[:total].copy_(src, non_blocking=True)
-                        ev = torch.cuda.Event()
+                        ev = torch.cuda.Event(enable_timing=True)
                         ev.record(copy_stream)
+                    copy_events.append((ev0, ev, 4 * total))
                     ready_q.put((j, StagedBatch(audio=sl.dev[: max(total, 4)], off=off.copy(), length=ln.copy(), sr=sr,
                                                 h2d_bytes=4 * total), ev, sl))
             except BaseException as e:  # noqa: BLE001
@@ -502,6 +510,11 @@ def analyse_batch(source, sr: int = SAMPLE_RATE, *, sub_batch: int = SUB_BATCH_P
             main.wait_stream(_worker_stream(device, w))
     if errors:
         raise errors[0]
+    if stats is not None and copy_events:
+        copy_events[-1][1].synchronize()
+        ms = sum(a.elapsed_time(b) for a, b, _ in copy_events)
+        stats["h2d_copy_ms"] = stats.get("h2d_copy_ms", 0.0) + ms          # time the copy engine spent on the uploads
+        stats["h2d_copy_gbs"] = sum(n for _, _, n in copy_events) / max(ms, 1e-9) / 1e6
     results: list = []
     for res, s1 in out:
         results += res

@@ -14,7 +14,7 @@ torch.cuda.set_device(0)
 distinct = bench.make_pairs(range(32), 180.0)
 pairs_np = [distinct[i % 32] for i in range(pairs)]
 pinned = nbatch.pin_pairs(pairs_np, 22050)
-sizes = nbatch.stagger_sizes(pairs, 125, workers)
+sizes = nbatch.stagger_sizes(pairs, min(125, max(16, -(-pairs // 4))), workers)
 starts = [sum(sizes[:j]) for j in range(len(sizes))]
 resident = [nbatch.upload(pinned, k, start_pair=s) for s, k in zip(starts, sizes)]
 for _ in range(2):
