@@ -217,6 +217,11 @@ def run_gpu(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local_rank)
+    cpus_local = []
+    if world > 1 and not os.environ.get("NCFA_NO_NUMA_BIND"):
+        sys.path.insert(0, os.path.join(ROOT, "nightcore-to-flac-analyzer_b200"))
+        from nightcore_analyzer import parallel as _npar
+        cpus_local = _npar.bind_to_gpu_cpus(local_rank)   # pinned buffers on the GPU's own NUMA node
     # torchrun exports OMP_NUM_THREADS=1 to every rank, which makes the pageable → pinned staging copy of
     # run_batch(list of numpy arrays) single-threaded; give every rank its share of the host cores instead
     torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(1, world)))
@@ -352,6 +357,7 @@ def run_gpu(args):
             "config": workload_config(total_pairs, args.pair_sec),
             "schedule": {"sub_batch_pairs": sub, "resident_sub_batches": sizes, "e2e_sub_batches": stats_e.get("sub_batches"),
                          "host_workers": args.workers, "windows_per_step": windows, "pairs_ok": n_ok,
+                         "rank0_cpu_affinity": len(cpus_local) or None,
                          "pitch": not args.no_pitch, "ibi": not args.no_ibi,
                          "resident_audio_mb_per_rank": round(resident_bytes / 1e6, 1)},
             "e2e": {"value": windows_e / (ms_e2e / 1e3), "unit": "windows/s", "ms_per_step": ms_e2e,

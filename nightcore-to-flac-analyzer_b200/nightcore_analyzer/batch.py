@@ -19,6 +19,7 @@ exception object in the result list and does not disturb the others.
 """
 from __future__ import annotations
 
+import os
 import queue
 import sys
 import threading
@@ -307,6 +308,17 @@ def plan_subbatches(n_pairs: int, sub: int, workers: int = 2, first: int = 8, gr
     sizes: List[int] = []
     left = int(n_pairs)
     sub = max(1, int(sub))
+    if 5 * first <= left <= 2 * sub and growth == 1.5:
+        # A batch of one or two jobs' worth (a rank's share of a 1000-pair batch on 8 GPUs): when several ranks upload at
+        # once the host feeds each GPU at ~37 GB/s instead of 55 and the call becomes upload bound — it then ends one job
+        # after the last byte arrives, so the LAST job must be short as well as the first.  Up, then down
+        # (measured on one GPU, 125 pairs: 12/24/40/29/20 → 878 pairs/s, 8/12/18/27/60 → 886, i.e. free when compute bound).
+        shape = (0.10, 0.19, 0.32, 0.23, 0.16)
+        sizes = [max(1, int(round(f * left))) for f in shape]
+        sizes[2] += left - sum(sizes)
+        if all(0 < k <= sub for k in sizes):
+            return sizes
+        sizes = []
     s = float(max(1, first))
     while left > 0 and int(s) < sub:
         k = min(int(s), left)
@@ -407,6 +419,10 @@ def analyse_batch(source, sr: int = SAMPLE_RATE, *, sub_batch: int = SUB_BATCH_P
         lengths = np.array([len(t) for t in tracks], dtype=np.int64)
     if P == 0:
         return []
+    if sizes is None and os.environ.get("NCFA_E2E_SIZES"):       # explicit plan (experiments): "8,12,18,..." must sum to P
+        sizes = [int(x) for x in os.environ["NCFA_E2E_SIZES"].split(",")]
+        if sum(sizes) != P:
+            sizes = None
     if sizes is None:
         sizes = [P] if P <= INLINE_PAIRS else plan_subbatches(P, sub_batch, workers, first=_first_job_pairs(P, sub_batch),
                                                               growth=_job_growth())

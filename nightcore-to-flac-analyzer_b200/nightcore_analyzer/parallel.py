@@ -10,6 +10,27 @@ import numpy as np
 RECORD_F64 = 16   # float64 slots per pair record
 
 
+def bind_to_gpu_cpus(device_index: int) -> List[int]:
+    """Restrict the calling process to the host cores NVML reports as local to GPU ``device_index`` (its NUMA node) and
+    return them ([] when NVML or the affinity call is unavailable — nothing changes then).  Call it before the first
+    pinned allocation: pinned pages are then first-touched on the GPU's own node, and with one process per GPU the
+    host→device copies of the ranks stop crossing the socket interconnect."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:  # noqa: BLE001 — an optimisation only
+        return []
+
+
 def shard_indices(n_pairs: int, rank: int, world: int) -> List[int]:
     return list(range(rank, n_pairs, world))
 

@@ -68,3 +68,13 @@ def test_shard_indices_cover_and_balance():
             parts = [npar.shard_indices(n, r, w) for r in range(w)]
             assert sorted(i for p in parts for i in p) == list(range(n))
             assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_numa_binding_is_a_no_op_without_nvml():
+    """parallel.bind_to_gpu_cpus is an optimisation: without a driver it must change nothing and raise nothing."""
+    import os
+    from nightcore_analyzer import parallel
+    before = os.sched_getaffinity(0)
+    cpus = parallel.bind_to_gpu_cpus(0)
+    assert isinstance(cpus, list)
+    assert os.sched_getaffinity(0) == (set(cpus) if cpus else before)
