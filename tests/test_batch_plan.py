@@ -36,3 +36,19 @@ def test_gil_handoff_is_restored():
     with batch._fast_gil_handoff():
         assert sys.getswitchinterval() <= 2e-4
     assert sys.getswitchinterval() == before
+
+
+@pytest.mark.parametrize("n", [40, 60, 125, 130, 200, 250])
+def test_small_batches_stream_up_then_down(n):
+    """A batch of one or two jobs' worth (a rank's share of 1000 pairs on 8 GPUs) is streamed as five jobs that grow and
+    then shrink: the first upload is the only exposed one, and the call ends a short job after the last byte arrives."""
+    sizes = batch.plan_subbatches(n, 125)
+    assert sum(sizes) == n and len(sizes) == 5 and all(s > 0 for s in sizes)
+    assert sizes[0] < sizes[1] < sizes[2] > sizes[3] > sizes[4]
+    assert sizes[0] <= max(1, round(0.12 * n)) and sizes[4] <= round(0.2 * n)
+
+
+def test_large_batches_keep_the_ramp():
+    assert batch.plan_subbatches(1000, 125)[:7] == [8, 12, 18, 27, 40, 60, 91]
+    assert batch.plan_subbatches(251, 125)[0] == 8            # just above two jobs' worth: the plain ramp
+    assert batch.plan_subbatches(39, 125) == [8, 12, 19]      # below five first-jobs: ramp with the remainder folded in
