@@ -763,12 +763,10 @@ constexpr int kTcQ = 2;                                  // column splits of a k
 constexpr int kTcVals = kTcKT / kTcQ;                    // samples per thread per k-tile (16)
 constexpr int kTcFrameWarps = 4 * kTcQ;
 constexpr int kTcThreads = (kTcFrameWarps + 2) * 32;     // 320
-constexpr int kTcAStages = 5;
+constexpr int kTcAStages = 5;                           // deep shape (TcOne); the default TcTwo uses 2
 constexpr int kTcBStages = kTcAStages;                   // A and B share the stage index and ONE release barrier per stage
 constexpr int kTcACols = 2 * kTcKT;                      // hi + lo columns of one A stage
-constexpr int kTcAccCol0 = kTcAStages * kTcACols;        // 320
 constexpr int kTcAccN = kTcN;                            // accumulator columns (80: 36 real, 36 imaginary, 8 pad)
-constexpr int kTcTmemCols = 512;                         // 320 (A ring) + 2 × 80 (accumulators)
 constexpr int kTcAPre = 4;                               // k-tiles of A rows in flight (cp.async ring in shared memory)
 constexpr int kTcAPlane = kTcFrames + 1;                 // float4 per chunk plane of the A staging ring
 
