@@ -354,7 +354,7 @@ def _job_growth() -> float:
 
 # ------------------------------------------------------------------------------------------------ the batch scheduler
 # One stager thread walks the jobs (consecutive, disjoint slices of the batch) in order: it lays a slice out in pinned
-# memory when the caller's arrays are pageable, queues its host→HBM copy on a copy stream into one of `workers + 1`
+# memory when the caller's arrays are pageable, queues its host→HBM copy on a copy stream into one of `workers + 2`
 # preallocated device slots and hands (StagedBatch, copy-done event) to whichever of the `workers` analysis threads is
 # free.  Each analysis thread has its own CUDA stream and Engine (workspaces, pinned parameter ring), so while one waits
 # for a small device→host read or assembles results the other keeps the GPU fed, and copies never sit in front of kernels.
@@ -464,7 +464,11 @@ def analyse_batch(source, sr: int = SAMPLE_RATE, *, sub_batch: int = SUB_BATCH_P
     nw = max(1, min(int(workers), len(sizes)))
     need = max(_layout(lengths[2 * s : 2 * (s + k)])[1] for s, k in zip(starts, sizes))
     with _SCHED_LOCK:       # one scheduled batch per process at a time (the slots are shared)
-        slots = _slots_for(device, nw + 1, need, want_pinned=not pinned_in)
+        # device slots: one per worker + TWO ahead.  With one ahead the copy of job j+3 cannot start before job j ends, and
+        # a worker that finishes early finds nothing uploaded: measured 1036 pairs/s with 3 slots, 1218 with 4, 1227 with 6
+        # (profiles/r3a_e2e_slots.log; 3.6 GB of HBM per slot at 125 pairs)
+        n_slots = int(os.environ.get("NCFA_E2E_SLOTS", 0)) or nw + 2
+        slots = _slots_for(device, n_slots, need, want_pinned=not pinned_in)
         free_q: "queue.Queue[_Slot]" = queue.Queue()
         for sl in slots:
             sl.free.record(main)
