@@ -216,6 +216,11 @@ def run_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    blocking = False
+    if os.environ.get("NCFA_BLOCKING_SYNC"):   # experiment only: measured slower (profiles/r3d_blocking_sync.log)
+        sys.path.insert(0, os.path.join(ROOT, "nightcore-to-flac-analyzer_b200"))
+        from nightcore_analyzer import parallel as _npar0
+        blocking = _npar0.use_blocking_sync(local_rank)
     torch.cuda.set_device(local_rank)
     cpus_local = []
     if world > 1 and not os.environ.get("NCFA_NO_NUMA_BIND"):
@@ -357,7 +362,7 @@ def run_gpu(args):
             "config": workload_config(total_pairs, args.pair_sec),
             "schedule": {"sub_batch_pairs": sub, "resident_sub_batches": sizes, "e2e_sub_batches": stats_e.get("sub_batches"),
                          "host_workers": args.workers, "windows_per_step": windows, "pairs_ok": n_ok,
-                         "rank0_cpu_affinity": len(cpus_local) or None,
+                         "rank0_cpu_affinity": len(cpus_local) or None, "blocking_sync": bool(blocking),
                          "pitch": not args.no_pitch, "ibi": not args.no_ibi,
                          "resident_audio_mb_per_rank": round(resident_bytes / 1e6, 1)},
             "e2e": {"value": windows_e / (ms_e2e / 1e3), "unit": "windows/s", "ms_per_step": ms_e2e,

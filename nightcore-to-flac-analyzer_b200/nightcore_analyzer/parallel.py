@@ -31,6 +31,23 @@ def bind_to_gpu_cpus(device_index: int) -> List[int]:
         return []
 
 
+def use_blocking_sync(device_index: int) -> bool:
+    """Make host threads that wait for ``device_index`` sleep instead of spin (cudaDeviceScheduleBlockingSync).  Must run
+    before the process creates its CUDA context on that device; returns False (and changes nothing) if the runtime
+    refuses.  NOT used by default: the hypothesis that spinning waits starve the ranks' Python threads at N = 8 did not
+    hold — a rank restricted to 4 (2) host cores runs its 125-pair share end to end at 920 (835) pairs/s with spinning
+    waits and at 866 (733) with blocking ones (profiles/r3d_blocking_sync.log)."""
+    import ctypes
+    try:
+        import torch  # noqa: F401 — loads the CUDA runtime this process will use
+        rt = ctypes.CDLL("libcudart.so.12")
+        if rt.cudaSetDevice(int(device_index)) != 0:
+            return False
+        return rt.cudaSetDeviceFlags(4) == 0          # cudaDeviceScheduleBlockingSync
+    except Exception:  # noqa: BLE001 — an optimisation only
+        return False
+
+
 def shard_indices(n_pairs: int, rank: int, world: int) -> List[int]:
     return list(range(rank, n_pairs, world))
 
