@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(128) tg_flags_kernel(const int32_t *__restrict
 
 // pass 2: partial[seg][chunk][k] = Σ_{t in chunk} R_t[k] / R_t[0] for the lags k in todo[seg] \ done[seg] (exact
 // intervals; CTA b covers todo.x + 128·b …, warps without a live lag leave at once).  One thread = one lag.
-__global__ void __launch_bounds__(kLagThreads) tg_lag_kernel(const float *__restrict__ onset,
+__global__ void __launch_bounds__(kLagThreads, 7) tg_lag_kernel(const float *__restrict__ onset,
                                                              const int64_t *__restrict__ onset_off,
                                                              const int32_t *__restrict__ env_len, int env_stride,
                                                              int W, int chunk, int n_chunks,
@@ -210,14 +210,20 @@ __global__ void __launch_bounds__(kLagThreads) tg_lag_kernel(const float *__rest
     const int n = env_len[seg];
     const int t0 = blockIdx.y * chunk;
     if (t0 >= n) return;
+    // A CTA serves the lag blocks blockIdx.x, blockIdx.x + gridDim.x, … of its (chunk, segment): the live lag range is
+    // data dependent — 1-2 blocks of the 22 in phase 1, usually none in phase 2 — and a grid with one CTA per possible
+    // block spent ~1 ms per launch scheduling CTAs that return at once (88 000 CTAs per 250 tracks, ncu r3e).
     const int2 td = todo[seg];
-    const int kb = td.x + blockIdx.x * kLagThreads;
-    if (kb >= td.y || kb >= W) return;
     int2 dn = make_int2(0, 0);
-    if (done != nullptr) {
-        dn = done[seg];
-        if (kb >= dn.x && min(kb + kLagThreads, td.y) <= dn.y) return;
-    }
+    if (done != nullptr) dn = done[seg];
+    auto block_live = [&](int kb) { return !(done != nullptr && kb >= dn.x && min(kb + kLagThreads, td.y) <= dn.y); };
+    bool any = false;
+    for (int kb = td.x + (int)blockIdx.x * kLagThreads; kb < td.y && kb < W; kb += (int)gridDim.x * kLagThreads)
+        if (block_live(kb)) {
+            any = true;
+            break;
+        }
+    if (!any) return;  // CTA-uniform
     const int t1 = min(n, t0 + chunk);
     const float *on = onset + onset_off[seg];
     const int p = W / 2;
@@ -227,18 +233,20 @@ __global__ void __launch_bounds__(kLagThreads) tg_lag_kernel(const float *__rest
         xs[i] = (m < n + 2 * p) ? (float)padded_env(on, n, p, m) : 0.0f;
     }
     __syncthreads();
+    const double *ri = r0inv + (size_t)seg * env_stride;
+    const double2 e1 = trig[1 % W], e2 = trig[2 % W];
+    for (int kb = td.x + (int)blockIdx.x * kLagThreads; kb < td.y && kb < W; kb += (int)gridDim.x * kLagThreads) {
+    if (!block_live(kb)) continue;
     const int k = kb + threadIdx.x;
     const bool active = k < td.y && k < W && !(k >= dn.x && k < dn.y);
-    if (!__any_sync(0xffffffffu, active)) return;
+    if (!__any_sync(0xffffffffu, active)) continue;  // no barrier below: warps of a CTA are independent from here on
     // lanes without a live lag shadow the warp's first lag (live warps have kw < W): same trip counts, in-bounds reads
     const int kk = active ? k : kb + (int)(threadIdx.x & ~31u);
     const int L = W - kk;
     const double2 ek = trig[kk];
-    const double2 e1 = trig[1 % W], e2 = trig[2 % W];
     const double2 eL = trig[L % W], e2L = trig[(2 * L) % W];
     const double q0 = 0.25 * (1.0 + 0.5 * ek.x), q1r = -0.25 * (1.0 + ek.x), q1i = 0.25 * ek.y,
                  q2r = 0.125 * ek.x, q2i = -0.125 * ek.y;
-    const double *ri = r0inv + (size_t)seg * env_stride;
     // the warp's longest window (smallest k) bounds the uniform rebuild loop
     const int Lmax = W - min(W - 1, kb + (int)(threadIdx.x & ~31u));
     double acc = 0.0;
@@ -291,6 +299,7 @@ __global__ void __launch_bounds__(kLagThreads) tg_lag_kernel(const float *__rest
         }
     }
     if (active) partial[((size_t)seg * n_chunks + blockIdx.y) * W + k] = acc;
+    }  // lag blocks of this CTA
 }
 
 __device__ __forceinline__ double tg_score(const double *__restrict__ partial, int seg, int n_chunks, int used_chunks,
@@ -525,7 +534,8 @@ extern "C" int ncfa_tempo_lag_batched(const float *d_onset, const int64_t *d_ons
             tg_flags_kernel<<<(warps + 3) / 4, 128, 0, st>>>(d_env_len, max_env_len, chunk, n_chunks, n_seg, r0, r0inv);
         }
         NCFA_LAUNCH_OK("tg_flags_kernel");
-        dim3 g((W - k_min + kLagThreads - 1) / kLagThreads, n_chunks, n_seg);
+        const int lag_blocks = (W - k_min + kLagThreads - 1) / kLagThreads;
+        dim3 g(lag_blocks < 2 ? lag_blocks : 2, n_chunks, n_seg);   // a CTA strides over the lag blocks (see the kernel)
         {
             ProfScope _p(n_chunks > 1 ? "tg_lag_kernel[long]" : "tg_lag_kernel", st);
             tg_lag_kernel<<<g, kLagThreads, sh, st>>>(d_onset, d_onset_off, d_env_len, max_env_len, W, chunk, n_chunks, trig,
