@@ -1,0 +1,113 @@
+"""CPU stand-in for ``nightcore_analyzer._engine.Engine`` — TEST INFRASTRUCTURE.
+
+Same method contracts as the real engine (names, argument meaning, return shapes and dtypes), but every "device"
+tensor is a CPU torch tensor and the arithmetic is the oracle's (oracle/librosa_restated.py, oracle/native.py).  It lets
+the ``-m "not gpu"`` tier execute the product's HOST logic — io / tempo / pitch / consensus / pipeline and the batch
+path of batch.analyse_staged: segment tables, gating, priors, log lines, result assembly — end to end without a GPU,
+against the same golden vectors the CUDA path is held to.  Nothing in the product imports this file."""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from oracle import librosa_restated as lr
+from oracle import native
+
+
+class FakeEngine:
+    device = torch.device("cpu")
+
+    def __init__(self):
+        self.launches = 0
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    # ---- transfers
+    def to_dev(self, a, dtype=None) -> torch.Tensor:
+        t = torch.from_numpy(np.ascontiguousarray(a).copy())
+        return t if dtype is None else t.to(dtype)
+
+    def to_host(self, t: torch.Tensor) -> np.ndarray:
+        self.d2h_bytes += t.numel() * t.element_size()
+        return t.cpu().numpy()
+
+    def pack(self, arrays: Sequence[np.ndarray]) -> Tuple[torch.Tensor, np.ndarray, np.ndarray]:
+        lens = np.array([len(a) for a in arrays], dtype=np.int32)
+        starts = np.zeros(len(arrays), dtype=np.int64)
+        pos = 0
+        for i, n in enumerate(lens):
+            starts[i] = pos
+            pos += (int(n) + 3) // 4 * 4
+        host = torch.zeros(max(pos, 4), dtype=torch.float32)
+        for a, s, n in zip(arrays, starts, lens):
+            host.numpy()[s : s + n] = np.asarray(a, dtype=np.float32)
+        return host, starts, lens
+
+    @staticmethod
+    def _seg(audio: torch.Tensor, off, ln) -> np.ndarray:
+        return audio.numpy()[int(off) : int(off) + int(ln)]
+
+    # ---- io.py
+    def window_energy_dev(self, audio, seg_off: torch.Tensor, seg_len: torch.Tensor) -> torch.Tensor:
+        out = [float(np.mean(self._seg(audio, o, n).astype(np.float64) ** 2)) if int(n) else 0.0
+               for o, n in zip(seg_off.tolist(), seg_len.tolist())]
+        return torch.tensor(out, dtype=torch.float64)
+
+    def trim_bounds_dev(self, audio, seg_off: np.ndarray, seg_len: np.ndarray, top_db: float) -> torch.Tensor:
+        out = np.zeros((len(seg_len), 2), dtype=np.int64)
+        for i, (o, n) in enumerate(zip(seg_off, seg_len)):
+            _, (s, e) = lr.trim(self._seg(audio, o, n), top_db=top_db)
+            out[i] = (s, e)
+        return torch.from_numpy(out)
+
+    # ---- tempo.py
+    def tempo_segments_dev(self, audio, seg_off: np.ndarray, seg_len: np.ndarray, start_bpm: np.ndarray, hop: int, sr: int):
+        lags, beats = [], []
+        for o, n, bpm in zip(seg_off, seg_len, np.asarray(start_bpm, dtype=np.float64)):
+            env = lr.onset_strength(self._seg(audio, o, n), sr, hop)
+            lag = int(lr.tempo_lag(env, sr, hop, float(bpm)))
+            lags.append(lag)
+            beats.append(np.asarray(lr.beat_track_frames(env, 60.0 * sr / (hop * float(lag)), sr, hop), dtype=np.int32)
+                         if lag > 0 else np.zeros(0, np.int32))
+        width = max([len(b) for b in beats] + [1])
+        table = np.zeros((len(beats), width), dtype=np.int32)
+        for i, b in enumerate(beats):
+            table[i, : len(b)] = b
+        n_beats = np.array([len(b) for b in beats], dtype=np.int32)
+        return None, None, None, torch.tensor(lags, dtype=torch.int32), torch.from_numpy(table), torch.from_numpy(n_beats)
+
+    def tempo_and_beats(self, arrays, start_bpm, hop: int, sr: int, want_beats: bool = True):
+        audio, off, ln = self.pack(arrays)
+        _, _, _, lag, beats, n_beats = self.tempo_segments_dev(audio, off, ln, np.asarray(start_bpm, np.float64), hop, sr)
+        hl, hn, hb = lag.numpy(), n_beats.numpy(), beats.numpy()
+        if not want_beats:
+            return hl, hn
+        return hl, [hb[i, : hn[i]].copy() for i in range(len(arrays))]
+
+    # ---- pitch.py
+    def chroma_mean_dev(self, audio, seg_off: np.ndarray, seg_len: np.ndarray, sr: int, tuning_idx=None):
+        rows = [lr.chroma_cqt(self._seg(audio, o, n), sr, 512, 36).mean(axis=1) for o, n in zip(seg_off, seg_len)]
+        return torch.from_numpy(np.asarray(rows, dtype=np.float64).reshape(len(rows), 12)), None
+
+    def cyclic_xcorr_dev(self, src: torch.Tensor, nc: torch.Tensor) -> torch.Tensor:
+        lags = []
+        for a, b in zip(src.numpy(), nc.numpy()):
+            n = len(a)
+            xc = np.array([float(np.dot(a, np.roll(b, -k))) for k in range(n)])
+            lag = int(np.argmax(xc))
+            lags.append(lag - n if lag > n // 2 else lag)
+        return torch.tensor(lags, dtype=torch.int32)
+
+    # ---- consensus.py / pitch.py bootstraps
+    def bootstrap(self, jobs, seed: int, n_boot: int, q_lo: float, q_hi: float, want_boot: bool = False,
+                  want_idx: bool = False):
+        out = np.zeros((len(jobs), 3))
+        for j, (a, b) in enumerate(jobs):
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            b = None if b is None else np.ascontiguousarray(b, dtype=np.float64)
+            boot = native.bootstrap(a, b, n_boot, seed)
+            point = float(np.median(a)) if b is None else float(np.median(a) / np.median(b))
+            out[j] = (point, float(np.percentile(boot, q_lo)), float(np.percentile(boot, q_hi)))
+        return out, None, None

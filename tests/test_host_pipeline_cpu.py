@@ -1,0 +1,111 @@
+"""CPU: the product's HOST logic end to end on an oracle-backed stand-in engine (tests/fake_engine.py).
+
+The drop-in modules (io / tempo / pitch / consensus / pipeline) and the batch path (batch.analyse_staged) build segment
+tables, gate windows, derive priors, format the reference's log lines and assemble AnalysisResult objects on the host;
+only the arithmetic is on the device.  With the engine replaced by one that computes the same quantities with the
+oracle, that host logic is held — without a GPU — to the golden vectors produced by the reference's own modules
+(tests/golden/pipeline_golden.json): every value via float.hex, every log line, str(result)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import fromhex
+from fake_engine import FakeEngine
+from oracle import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SR = 22050
+
+
+def unhex(v):
+    return None if v is None else fromhex(v)
+
+
+@pytest.fixture(scope="module")
+def golden():
+    with open(os.path.join(ROOT, "tests", "golden", "pipeline_golden.json")) as f:
+        return json.load(f)["pipeline_A"]
+
+
+@pytest.fixture()
+def fake(monkeypatch):
+    from nightcore_analyzer import _engine
+    eng = FakeEngine()
+    monkeypatch.setattr(_engine, "get_engine", lambda device=None: eng)
+    return eng
+
+
+@pytest.fixture(scope="module")
+def pair_a():
+    src, nc = synth.make_pair(1000, 45.0, SR)
+    return nc, src
+
+
+def check_against_golden(res, A):
+    assert res.src_tempos_raw == [unhex(v) for v in A["src_tempos"]]
+    assert res.nc_tempos_raw == [unhex(v) for v in A["nc_tempos"]]
+    assert res.nc_pitches_raw == [unhex(v) for v in A["nc_hz"]] and res.src_pitches_raw == [unhex(v) for v in A["src_hz"]]
+    assert res.tempo_ratio == unhex(A["tempo_ratio"]) and list(res.tempo_ci) == [unhex(v) for v in A["tempo_ci"]]
+    assert res.pitch_ratio == unhex(A["pitch_ratio"]) and list(res.pitch_ci) == [unhex(v) for v in A["pitch_ci"]]
+    assert res.ibi_ratio == unhex(A["ibi_ratio"]) and list(res.ibi_ci) == [unhex(v) for v in A["ibi_ci"]]
+    assert res.classification == A["classification"] and res.pitch_method == A["pitch_method"]
+    assert res.warnings == A["warnings"] and res.rubberband == A["rubberband"]
+    assert str(res) == A["str"]
+    assert [res.n_source_pitch_windows, res.n_nc_pitch_windows, res.n_source_tempo_windows,
+            res.n_nc_tempo_windows] == A["n"]
+
+
+def test_run_arrays_host_logic_matches_reference_flow(fake, pair_a, golden):
+    """pipeline.run_arrays → io / pitch / tempo / consensus drop-ins, stage order and log lines of pipeline.py:91-216."""
+    import nightcore_analyzer as na
+    nc, src = pair_a
+    logs = []
+    res = na.run_arrays(nc, src, SR, log=logs.append)
+    check_against_golden(res, golden)
+    ref_logs = golden["logs"][golden["logs"].index(next(m for m in golden["logs"] if m.startswith("Stripping silence"))):]
+    assert logs == ref_logs
+
+
+def test_batch_path_host_logic_equals_the_single_pair_path(fake, pair_a, golden):
+    """batch.analyse_staged is pipeline.run turned inside out (every stage once over all pairs): on the same engine it
+    must give the single-pair results — here for a batch that also holds a pair the energy gate empties and a pair too
+    short for any window, which must fail alone without disturbing the others."""
+    from nightcore_analyzer import batch
+    nc, src = pair_a
+    silent = np.zeros(30 * SR, np.float32)
+    short = synth.synth(5, 4.0, SR, bpm=100.0)
+    tracks = [nc, src, silent, silent, nc, src, short, short]
+    audio, off, ln = fake.pack(tracks)
+    st = batch.StagedBatch(audio=audio, off=off, length=ln.astype(np.int64), sr=SR, h2d_bytes=0)
+    stats = {}
+    out = batch.analyse_staged(st, stats=stats)
+    assert len(out) == 4
+    check_against_golden(out[0], golden)
+    check_against_golden(out[2], golden)
+    assert out[0].intro_offset_sec is None
+    # the failing pairs fail exactly as they do alone through run_arrays (same exception type and message)
+    import nightcore_analyzer as na
+    for k, (a, b) in ((1, (silent, silent)), (3, (short, short))):
+        with pytest.raises(Exception) as alone:
+            na.run_arrays(a, b, SR, log=None)
+        assert type(out[k]) is type(alone.value) and str(out[k]) == str(alone.value)
+    assert isinstance(out[3], RuntimeError) and "All windows were discarded by the energy gate" in str(out[3])
+    assert isinstance(out[1], ValueError) and "Insufficient valid tempo windows" in str(out[1])
+    # analysed windows: the two good pairs + the 5 + 5 windows of the all-zero pair (equal energies: the gate keeps them all)
+    assert stats["tracks"] == 8 and stats["windows"] == 2 * (len(golden["src_tempos"]) + len(golden["nc_tempos"])) + 10
+
+
+def test_no_pitch_and_manual_trim_flow(fake, pair_a):
+    """compute_pitch=False and src_trim_sec (pipeline.py:106-112, 148-159): log lines and fields of the reference."""
+    import nightcore_analyzer as na
+    nc, src = pair_a
+    logs = []
+    res = na.run_arrays(nc, np.concatenate([np.zeros(2 * SR, np.float32) + 1e-3, src]), SR, src_trim_sec=2.0,
+                        silence_strip_db=None, compute_pitch=False, log=logs.append)
+    assert res.intro_offset_sec == 2.0 and res.pitch_method is None
+    assert res.src_pitches_raw == [] and res.nc_pitches_raw == [] and res.pitch_ratio == 1.0
+    assert "Manual source trim: skipping 2.00s from source start" in logs and "Skipping pitch estimation." in logs
+    assert not any(m.startswith("Stripping silence") for m in logs) and logs[-1] == "Done."
