@@ -111,3 +111,29 @@ class FakeEngine:
             point = float(np.median(a)) if b is None else float(np.median(a) / np.median(b))
             out[j] = (point, float(np.percentile(boot, q_lo)), float(np.percentile(boot, q_hi)))
         return out, None, None
+
+    # ---- xcorr.py: the candidate loop of estimate_speed_xcorr (xcorr.py:113-148), float32 dots like numpy's
+    def xcorr_search_dev(self, a, b, a_pos: np.ndarray, b_lo: np.ndarray, n_cand: np.ndarray, win: int, stride: int,
+                         rms_gate: float):
+        ya, yb = a.numpy(), b.numpy()
+        best_j = np.full(len(a_pos), -1, dtype=np.int32)
+        best_c = np.zeros(len(a_pos), dtype=np.float64)
+        for w, (pa, lo, nc) in enumerate(zip(a_pos, b_lo, n_cand)):
+            wa = ya[int(pa) : int(pa) + win]
+            if float(np.sqrt(np.mean(wa ** 2))) < rms_gate:
+                continue
+            norm_a = float(np.linalg.norm(wa))
+            if norm_a < 1e-10:
+                continue
+            best, bj = -1.0, -1
+            for j in range(int(nc)):
+                wb = yb[int(lo) + j * stride : int(lo) + j * stride + win]
+                norm_b = float(np.linalg.norm(wb))
+                if norm_b < 1e-10:
+                    continue
+                c = float(np.dot(wa, wb)) / (norm_a * norm_b)
+                if c > best:
+                    best, bj = c, j
+            if bj >= 0 and best > 0.0:
+                best_j[w], best_c[w] = bj, best
+        return torch.from_numpy(best_j), torch.from_numpy(best_c)

@@ -109,3 +109,21 @@ def test_no_pitch_and_manual_trim_flow(fake, pair_a):
     assert res.src_pitches_raw == [] and res.nc_pitches_raw == [] and res.pitch_ratio == 1.0
     assert "Manual source trim: skipping 2.00s from source start" in logs and "Skipping pitch estimation." in logs
     assert not any(m.startswith("Stripping silence") for m in logs) and logs[-1] == "Done."
+
+
+def test_xcorr_host_logic_matches_reference_flow(fake):
+    """xcorr.estimate_speed_xcorr_arrays: trimming, window / candidate tables, polyfit slope and median quality
+    (xcorr.py:95-162) on the stand-in engine vs the reference's own result for the same pair."""
+    import scipy.signal
+    from nightcore_analyzer import xcorr as nx
+    with open(os.path.join(ROOT, "tests", "golden", "pipeline_golden.json")) as f:
+        C = json.load(f)["xcorr_C"]
+    a = synth.synth(4000, 120.0, SR, bpm=124.0)
+    b = scipy.signal.resample_poly(a, 1000, 1003).astype(np.float32)
+    b = (b + np.random.default_rng(4000).standard_normal(len(b)).astype(np.float32) * 0.01).astype(np.float32)
+    ratio, quality = nx.estimate_speed_xcorr_arrays(a, b, SR)
+    assert ratio == unhex(C["ratio"])
+    assert abs(quality - unhex(C["quality"])) <= 1e-6
+    assert nx.quality_label(quality) == C["label"]
+    # too short for a single 3 s window after edge trimming: the reference's (1.0, 0.0) sentinel
+    assert nx.estimate_speed_xcorr_arrays(a[: 2 * SR], b[: 2 * SR], SR) == (1.0, 0.0)
