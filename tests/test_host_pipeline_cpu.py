@@ -127,3 +127,48 @@ def test_xcorr_host_logic_matches_reference_flow(fake):
     assert nx.quality_label(quality) == C["label"]
     # too short for a single 3 s window after edge trimming: the reference's (1.0, 0.0) sentinel
     assert nx.estimate_speed_xcorr_arrays(a[: 2 * SR], b[: 2 * SR], SR) == (1.0, 0.0)
+
+
+def test_run_from_files_emits_the_reference_log_from_its_first_line(fake, pair_a, golden, tmp_path):
+    """pipeline.run (pipeline.py:23-216) on .npy files: the complete log of the reference's own run, loading stanzas
+    included, and the same result object."""
+    import nightcore_analyzer as na
+    nc, src = pair_a
+    np.save(tmp_path / "nc.npy", nc)
+    np.save(tmp_path / "src.npy", src)
+    logs = []
+    res = na.run(str(tmp_path / "nc.npy"), str(tmp_path / "src.npy"), log=logs.append)
+    assert logs == golden["logs"]
+    check_against_golden(res, golden)
+    # log=None is silent and changes nothing
+    assert str(na.run(str(tmp_path / "nc.npy"), str(tmp_path / "src.npy"), log=None)) == golden["str"]
+
+
+def test_auto_align_branches(fake, pair_a, monkeypatch):
+    """pipeline.py:113-125: an intro offset at or above ALIGN_MIN_OFFSET trims the source and is reported; a smaller one is
+    only logged.  (find_content_offset itself is held to the reference on the GPU and in the oracle tests.)"""
+    import nightcore_analyzer as na
+    from nightcore_analyzer import pipeline, xcorr
+    nc, src = pair_a
+    padded = np.concatenate([synth.synth(9, 3.0, SR, bpm=90.0) * 0.2, src]).astype(np.float32)
+
+    monkeypatch.setattr(pipeline, "find_content_offset", lambda s, n, sr: (3.0, 1.2512))
+    logs = []
+    res = na.run_arrays(nc, padded, SR, auto_align=True, compute_pitch=False, silence_strip_db=None, log=logs.append)
+    assert res.intro_offset_sec == 3.0
+    assert logs[0] == "Detecting intro offset (RMS envelope alignment)…"
+    assert logs[1] == "  Intro detected — trimming 3.00s from source start  (speed hint: 1.2512×)"
+    assert res.src_duration == len(src) / SR
+
+    small = xcorr.ALIGN_MIN_OFFSET / 2
+    monkeypatch.setattr(pipeline, "find_content_offset", lambda s, n, sr: (small, 1.25))
+    logs = []
+    res = na.run_arrays(nc, src, SR, auto_align=True, compute_pitch=False, silence_strip_db=None, log=logs.append)
+    assert res.intro_offset_sec is None
+    assert logs[1] == (f"  No significant intro offset detected  (raw: {small:.2f}s < "
+                       f"{xcorr.ALIGN_MIN_OFFSET:.1f}s threshold)")
+    # a manual trim wins over auto-align and never calls the detector
+    monkeypatch.setattr(pipeline, "find_content_offset", lambda *a: (_ for _ in ()).throw(AssertionError("called")))
+    res = na.run_arrays(nc, padded, SR, src_trim_sec=3.0, auto_align=True, compute_pitch=False, silence_strip_db=None,
+                        log=None)
+    assert res.intro_offset_sec == 3.0
