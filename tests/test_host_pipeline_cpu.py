@@ -172,3 +172,22 @@ def test_auto_align_branches(fake, pair_a, monkeypatch):
     res = na.run_arrays(nc, padded, SR, src_trim_sec=3.0, auto_align=True, compute_pitch=False, silence_strip_db=None,
                         log=None)
     assert res.intro_offset_sec == 3.0
+
+
+def test_cli_single_pair_on_the_stand_in_engine(fake, pair_a, golden, tmp_path, capsys):
+    """cli.main → pipeline.run → export.cli_dict: exit code 0, the JSON of the reference's cli for this result; --quiet
+    prints nothing; an emptied gate is exit code 1 with the reference's message."""
+    from nightcore_analyzer import cli, export
+    import nightcore_analyzer as na
+    nc, src = pair_a
+    np.save(tmp_path / "nc.npy", nc)
+    np.save(tmp_path / "src.npy", src)
+    out = tmp_path / "res.json"
+    assert cli.main(["-n", str(tmp_path / "nc.npy"), "-s", str(tmp_path / "src.npy"), "-o", str(out), "--quiet"]) == 0
+    assert capsys.readouterr().out == ""
+    want = na.run_arrays(nc, src, SR, log=None)
+    assert out.read_text(encoding="utf-8") == json.dumps(export.cli_dict(want), indent=2)
+    assert str(want) == golden["str"]
+    np.save(tmp_path / "short.npy", synth.synth(3, 4.0, SR, bpm=100.0))
+    assert cli.main(["-n", str(tmp_path / "short.npy"), "-s", str(tmp_path / "short.npy"), "-q"]) == 1
+    assert "ERROR: All windows were discarded by the energy gate." in capsys.readouterr().err
