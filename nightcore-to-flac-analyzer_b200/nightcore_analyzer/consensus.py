@@ -138,7 +138,7 @@ def _median_small(values) -> float:
     """np.median of a short 1-D sequence of finite float64 values, bit for bit (middle element, or the mean of the two
     middle elements computed as (a + b) / 2 like np.mean of two values) without numpy's per-call overhead — the batch
     path takes a few medians per pair, 150 µs of interpreter time each way through np.median."""
-    v = sorted(float(x) for x in values)
+    v = sorted(values.tolist() if isinstance(values, np.ndarray) else [float(x) for x in values])
     n = len(v)
     h = n >> 1
     return v[h] if n & 1 else (v[h - 1] + v[h]) / 2.0
