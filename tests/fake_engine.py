@@ -137,3 +137,21 @@ class FakeEngine:
             if bj >= 0 and best > 0.0:
                 best_j[w], best_c[w] = bj, best
         return torch.from_numpy(best_j), torch.from_numpy(best_c)
+
+    # ---- xcorr.py: intro alignment (xcorr.py:206-252)
+    def align_envelope(self, audio: np.ndarray, sr: int, target_sr: int, hop: int) -> torch.Tensor:
+        return torch.from_numpy(lr.rms(lr.resample(audio, sr, target_sr), 2048, hop).astype(np.float64))
+
+    def align_search(self, src_env: torch.Tensor, nc_env: torch.Tensor, n_str: np.ndarray, n_lag: np.ndarray):
+        s, n = src_env.numpy(), nc_env.numpy()
+        peak = np.full(len(n_str), -1, dtype=np.int32)
+        score = np.zeros(len(n_str), dtype=np.float64)
+        for i, (ns, nl) in enumerate(zip(n_str, n_lag)):
+            if nl <= 0:
+                continue
+            stretched = np.interp(np.linspace(0.0, 1.0, int(ns)), np.linspace(0.0, 1.0, len(n)), n)
+            corr = np.correlate(s[: int(nl) - 1 + int(ns)], stretched, mode="valid")[: int(nl)]
+            pk = int(np.argmax(corr))
+            denom = np.sqrt(float(np.sum(s[pk : pk + int(ns)] ** 2)) * float(np.sum(stretched ** 2)))
+            peak[i], score[i] = pk, (float(corr[pk]) / denom if denom > 1e-12 else 0.0)
+        return peak, score

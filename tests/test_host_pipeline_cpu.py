@@ -191,3 +191,20 @@ def test_cli_single_pair_on_the_stand_in_engine(fake, pair_a, golden, tmp_path, 
     np.save(tmp_path / "short.npy", synth.synth(3, 4.0, SR, bpm=100.0))
     assert cli.main(["-n", str(tmp_path / "short.npy"), "-s", str(tmp_path / "short.npy"), "-q"]) == 1
     assert "ERROR: All windows were discarded by the energy gate." in capsys.readouterr().err
+
+
+def test_find_content_offset_host_logic_matches_reference_flow(fake):
+    """xcorr.find_content_offset: per-speed geometry (which speeds are skipped, search lengths), best-score selection and
+    the frames → seconds conversion (xcorr.py:165-259) against the reference's own answer for the same pair."""
+    import scipy.signal
+    from nightcore_analyzer import xcorr as nx
+    with open(os.path.join(ROOT, "tests", "golden", "pipeline_golden.json")) as f:
+        D = json.load(f)["align_D"]
+    body = synth.synth(77, 60.0, SR, bpm=110.0)
+    intro = synth.synth(78, 12.0, SR, bpm=90.0) * 0.3
+    src = np.concatenate([intro, body]).astype(np.float32)
+    nc = scipy.signal.resample_poly(body, 4, 5).astype(np.float32)
+    off, speed = nx.find_content_offset(src, nc, SR)
+    assert off == unhex(D["offset_sec"]) and float(speed) == unhex(D["speed"])
+    # a nightcore longer than the source at every candidate speed: nothing to search, the reference's neutral answer
+    assert nx.find_content_offset(nc[: 3 * SR], np.tile(nc, 3), SR) == (0.0, (nx.ALIGN_SPEED_LO + nx.ALIGN_SPEED_HI) / 2.0)
