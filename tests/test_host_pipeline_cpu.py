@@ -208,3 +208,23 @@ def test_find_content_offset_host_logic_matches_reference_flow(fake):
     assert off == unhex(D["offset_sec"]) and float(speed) == unhex(D["speed"])
     # a nightcore longer than the source at every candidate speed: nothing to search, the reference's neutral answer
     assert nx.find_content_offset(nc[: 3 * SR], np.tile(nc, 3), SR) == (0.0, (nx.ALIGN_SPEED_LO + nx.ALIGN_SPEED_HI) / 2.0)
+
+
+def test_verification_library_call_host_logic(fake):
+    """verify.verify_arrays (workflow.py:160-163, 299-400, 778-833 as a library call): a re-render of the same nightcore
+    (tiny added noise) must verify — IBI estimator, tempo and pitch within tolerance, no length warning, and the xcorr
+    verdict follows the 0.30 quality gate; a copy played 3 % faster must fail the tempo check, warn about the length and
+    report the corrective factor."""
+    import scipy.signal
+    from nightcore_analyzer import verify, xcorr as nx
+    ncog = synth.synth(31, 32.0, SR, bpm=150.0)
+    hqnc = (ncog + np.random.default_rng(5).standard_normal(len(ncog)).astype(np.float32) * 1e-3).astype(np.float32)
+    v = verify.verify_arrays(hqnc, ncog, SR)
+    assert v.estimator == "IBI" and v.tempo_ok and v.pitch_ok and not v.length_warn
+    assert v.result.pitch_method is None and v.corrected_speed_factor == v.best_ratio
+    assert (v.result.xcorr_ratio, v.result.xcorr_quality) == nx.estimate_speed_xcorr_arrays(hqnc, ncog, SR)
+    assert v.xcorr_discarded == ((v.result.xcorr_quality or 0.0) < verify.XCORR_QUALITY_GATE)
+    assert v.xcorr_label == (None if v.xcorr_discarded else nx.quality_label(v.result.xcorr_quality))
+    fast = scipy.signal.resample_poly(ncog, 100, 103).astype(np.float32)       # HQNC 3 % too fast
+    w = verify.verify_arrays(fast, ncog, SR)
+    assert not w.tempo_ok and w.length_warn and abs(w.best_ratio - 1 / 1.03) < 5e-3
