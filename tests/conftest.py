@@ -9,6 +9,11 @@ PKG_PARENT = os.path.join(ROOT, "nightcore-to-flac-analyzer_b200")
 for p in (ROOT, PKG_PARENT):
     if p not in sys.path:
         sys.path.insert(0, p)
+# an operator-provided install of the reference's dependency (librosa) under baseline/_ref switches on the
+# real-librosa tier (tests/test_real_librosa_tier.py); it goes LAST so that nothing else is shadowed
+_REF_SITE = os.path.join(ROOT, "baseline", "_ref")
+if os.path.isdir(_REF_SITE) and _REF_SITE not in sys.path:
+    sys.path.append(_REF_SITE)
 
 
 def pytest_configure(config):
